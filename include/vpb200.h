@@ -1,0 +1,185 @@
+/*
+ * libvpb200 -- C ABI of the B200-native BFM reconstruction + rasterization path.
+ *
+ * Drop-in scope (reference taylorlu/voicepuppet, paths relative to its root):
+ *   utils/cython/mesh_core_cython.pyx:40-99   render_colors_core, rasterize_triangles_core,
+ *                                             render_texture_core, get_normal_core
+ *   utils/reconstruct_mesh.py:5-223           Shape/Texture formation, Compute_norm,
+ *                                             Projection_layer, Illumination_layer,
+ *                                             Reconstruction, Reconstruction_rotation
+ *   voicepuppet/pixrefer/infer_bfmvid.py:76-122,231-243   the per-frame render loop
+ *
+ * Conventions
+ *   - every function returns 0 on success; on failure a non-zero code, and
+ *     vp_last_error() (thread local) describes it.  There is no CPU fallback: without a
+ *     CUDA device every compute entry point fails with VP_ERR_CUDA.
+ *   - plain pointers + sizes only.  Pointers are HOST pointers unless the name ends in
+ *     _dev or the parameter says "device".  The callee never keeps or frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Host-pointer
+ *     entry points synchronise before returning; _dev entry points only enqueue.
+ *   - indices are 0-based int32 (the Python shim converts the model's 1-based MATLAB
+ *     doubles exactly as the reference does with (x - 1).astype(np.int32)).
+ */
+#ifndef VPB200_H_
+#define VPB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_OK 0
+#define VP_ERR_ARG 1
+#define VP_ERR_CUDA 2
+#define VP_ERR_STATE 3
+
+#define VP_N_ID 80
+#define VP_N_EX 64
+#define VP_N_TEX 80
+#define VP_N_GAMMA 27
+#define VP_RING 8 /* point_buf slots per vertex */
+
+/* bit flags for vp_model_create(float64_mask): which float arrays are float64 */
+#define VP_F64_MEANSHAPE 1
+#define VP_F64_IDBASE 2
+#define VP_F64_EXBASE 4
+#define VP_F64_MEANTEX 8
+#define VP_F64_TEXBASE 16
+
+typedef struct vp_model vp_model; /* opaque: device-resident BFM model + workspaces */
+
+const char* vp_last_error(void);
+int vp_version(void);
+/* number of visible CUDA devices, or a negative VP_ERR code */
+int vp_device_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * mesh_core_cython replacements: caller-initialised buffers, mutated in place.
+ * --------------------------------------------------------------------------------------- */
+
+/* render_colors_core (mesh_core_cython.pyx:64-78 -> mesh_core.cpp:169-231).
+ * image[h*w*c] u8, face_mask[h*w] u8, vertices[3*nver] f32, triangles[3*ntri] i32,
+ * colors[c*nver] f32, depth_buffer[h*w] f32.  `nver` is new (the reference trusts the
+ * indices); it sizes the host->device copy.  triangle_id (may be NULL) receives the winning
+ * triangle per pixel, -1 where nothing was drawn (the reference never materialises it). */
+int vp_render_colors_core(unsigned char* image, unsigned char* face_mask, const float* vertices,
+                          const int* triangles, const float* colors, float* depth_buffer,
+                          int* triangle_id, int nver, int ntri, int h, int w, int c);
+
+/* rasterize_triangles_core (mesh_core_cython.pyx:49-62 -> mesh_core.cpp:108-166).
+ * vertices[nver*3], triangles[ntri*3], depth_buffer[h*w], triangle_buffer[h*w],
+ * barycentric_weight[h*w*3]. */
+int vp_rasterize_triangles_core(const float* vertices, const int* triangles, float* depth_buffer,
+                                int* triangle_buffer, float* barycentric_weight,
+                                int nver, int ntri, int h, int w);
+
+/* Batched device-pointer form of render_colors_core: `nframes` meshes sharing one triangle
+ * list.  vertices[nframes][3*nver], colors[nframes][c*nver], image[nframes][h*w*c],
+ * face_mask[nframes][h*w], depth_buffer[nframes][h*w], triangle_id (NULL ok)[nframes][h*w]. */
+int vp_render_colors_batch_dev(unsigned char* image, unsigned char* face_mask, const float* vertices,
+                               const int* triangles, const float* colors, float* depth_buffer,
+                               int* triangle_id, int nframes, int nver, int ntri, int h, int w, int c,
+                               int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Model object (utils/bfm_load_data.py:9-21) and reconstruction (utils/reconstruct_mesh.py)
+ * --------------------------------------------------------------------------------------- */
+
+/* meanshape[3N], idBase[3N][80], exBase[3N][64], meantex[3N], texBase[3N][80]: float32, or
+ * float64 where the matching VP_F64_* bit is set.  tri[ntri][3], point_buf[nver][8] with pad
+ * entries == ntri (i.e. the reference's F+1 after its "- 1").
+ * center: the 3 per-axis means of meanshape that reconstruct_mesh.py:27 subtracts; pass the
+ * host framework's value to reproduce its rounding, or NULL to have it computed here. */
+int vp_model_create(vp_model** out, int device, int nver, int ntri, const void* meanshape,
+                    const void* idBase, const void* exBase, const void* meantex,
+                    const void* texBase, int float64_mask, const int* tri, const int* point_buf,
+                    const double* center);
+void vp_model_destroy(vp_model* m);
+int vp_model_nver(const vp_model* m);
+int vp_model_ntri(const vp_model* m);
+
+/* Per-clip constants ("identity mean precomputed once"): base shape = meanshape + idBase.id
+ * - center, texture = meantex + texBase.tex.  Either pointer may be NULL to keep the old one. */
+int vp_set_identity(vp_model* m, const float* id_coeff80, const float* tex_coeff80);
+/* Replace the base shape by an explicit [nver][3] float64 array (stage-function callers). */
+int vp_set_base_shape(vp_model* m, const double* shape);
+/* Replace the texture by an explicit [nver][3] float32 array. */
+int vp_set_texture(vp_model* m, const float* texture);
+/* Copy out the current texture [nver][3] float32 / base shape [nver][3] float64. */
+int vp_get_texture(vp_model* m, float* texture);
+int vp_get_base_shape(vp_model* m, double* shape);
+
+/* Per-frame inputs of the batched entry points (all host, row-major):
+ *   ex[nframes][64]        expression coefficients; NULL = no expression displacement
+ *   rotation[nframes][9]   float64 row-major 3x3, the matrix of Compute_rotation_matrix
+ *   translation[nframes][3], gamma[nframes][27] float32
+ * rotate_shape_first: 0 = Reconstruction (reconstruct_mesh.py:172-194),
+ *                     1 = Reconstruction_rotation (:198-223: shape rotated, then projected
+ *                         with the same rotation again; normals rotated once). */
+typedef struct vp_frames {
+  int nframes;
+  const float* ex;
+  const double* rotation;
+  const float* translation;
+  const float* gamma;
+  int rotate_shape_first;
+  double focal;  /* 1015.0 */
+  double center; /* 112.0 */
+} vp_frames;
+
+/* Reconstruction outputs, any may be NULL; all [nframes][nver][k] in the model's vertex order.
+ *   face_shape f64[3] (rotated once when rotate_shape_first), face_norm f32[3] (unit normal
+ *   BEFORE rotation, as Compute_norm returns), face_color f32[3] (unclamped),
+ *   projection f64[2] = (x, image_size - y) when flip_y else (x, y), z_buffer f64[1]. */
+typedef struct vp_recon_out {
+  double* face_shape;
+  float* face_norm;
+  float* face_color;
+  double* projection;
+  double* z_buffer;
+  int flip_y;
+  double image_size; /* 224.0 */
+} vp_recon_out;
+
+int vp_reconstruct(vp_model* m, const vp_frames* frames, const vp_recon_out* out);
+
+/* Illumination_layer on caller-supplied texture/normals (reconstruct_mesh.py:129-168).
+ * texture[n][3], norm[n][3] float64, gamma[27] float32 -> color[n][3], lighting[n][3] float64. */
+int vp_illumination(int device, int n, const double* texture, const double* norm, const float* gamma,
+                    double* color, double* lighting);
+
+/* The whole hot path, coefficients -> rendered frames (infer_bfmvid.py:91-109 per frame):
+ * reconstruction, colours clipped to [0,255] and truncated, vertices (x, S - y, -z) scaled by
+ * res/224, flat-shaded z-buffer rasterization at h = w = res.
+ *   image[nframes][res][res][3] u8, face_mask[nframes][res][res] u8 (NULL ok).
+ * outputs_on_device: 0 = host pointers (copied back, pipelined per chunk), 1 = device pointers. */
+int vp_render_sequence(vp_model* m, const vp_frames* frames, int res, unsigned char* image,
+                       unsigned char* face_mask, int outputs_on_device, void* stream);
+
+/* Device-resident variant: per-frame inputs already on the device, packed as
+ * ex_dev[nframes][64] f32 and params_dev[nframes] of vp_frame_params; nothing is copied or
+ * synchronised.  This is what bench.py's device-resident `value` measures. */
+typedef struct vp_frame_params {
+  double rotation[9];
+  float translation[3];
+  float gamma[27];
+} vp_frame_params;
+
+int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev,
+                           const vp_frame_params* params_dev, int rotate_shape_first, int res,
+                           unsigned char* image_dev, unsigned char* face_mask_dev, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+unsigned long long vp_launch_count(void);
+
+/* Per-kernel device time of the last vp_render_sequence_dev call when profiling is enabled
+ * (CUDA events around each kernel, accumulated over chunks).  names: semicolon separated. */
+int vp_set_profiling(vp_model* m, int enabled);
+int vp_get_profile(vp_model* m, char* names, int names_cap, float* ms, int ms_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPB200_H_ */

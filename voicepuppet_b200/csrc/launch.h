@@ -1,0 +1,109 @@
+// Internal launch API between the translation units of libvpb200 (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <vector>
+
+#include "common.h"
+#include "vp_math.cuh"
+
+namespace vp {
+
+// ---- rasterizer (raster.cu) -----------------------------------------------------------
+int launch_keys_from_depth(const float* depth_dev, unsigned long long* keys_dev, size_t n, cudaStream_t st);
+int launch_scatter_generic(int mode, const float* vertices, size_t frame_stride, const int* triangles,
+                           unsigned long long* keys, int nframes, int ntri, int h, int w, cudaStream_t st);
+int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
+                          unsigned long long* keys, uint32_t* tri_color, int nframes, int ntri, int h, int w,
+                          cudaStream_t st);
+int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, unsigned char* image,
+                          unsigned char* mask, int nframes, int ntri, int h, int w, cudaStream_t st);
+
+// ---- vertex-tile topology (model.cu builds it, reconstruct.cu consumes it) -------------
+constexpr int kTileV = 128;    // own vertices per tile == threads per CTA of the vertex kernel
+constexpr int kTileLV = 384;   // own + halo vertices
+constexpr int kTileLT = 512;   // triangles touching the tile's own vertices
+constexpr uint16_t kRingPad = 0xFFFF;
+
+struct TileDesc {
+  int v_begin;   // first own vertex (internal order); own vertices are contiguous
+  int nv;        // own vertices
+  int nlv;       // local vertices (own first, then halo)
+  int nlt;       // local triangles
+  int halo_off;  // into halo[] (internal vertex ids of local vertices nv..nlv-1)
+  int ltri_off;  // into ltri[] (3 x 10-bit local vertex indices)
+};
+
+// Optional per-vertex outputs of the vertex kernel, in the MODEL's (original) vertex order.
+struct ReconOut {
+  double* shape = nullptr;   // [T][nver][3]
+  float* norm = nullptr;     // [T][nver][3]
+  float* color = nullptr;    // [T][nver][3]
+  double* proj = nullptr;    // [T][nver][2]
+  double* zbuf = nullptr;    // [T][nver]
+  int flip_y = 1;
+  double image_size = 224.0;
+};
+
+}  // namespace vp
+
+// The model object behind the opaque C handle.
+struct vp_model {
+  int device = 0;
+  int nver = 0, ntri = 0;
+  int rows = 0;         // 3 * nver
+  int row_stride = 0;   // floats per frame in the displacement buffer (rows rounded up to 32)
+  int vrec_stride = 0;  // float4 per frame in the vertex-record buffer
+  double center[3] = {0, 0, 0};
+
+  // host-side permutations (internal order is a Morton order of the mean shape)
+  std::vector<int> v_int2orig, v_orig2int, t_int2orig;
+
+  // device: model (internal vertex order)
+  float* exb = nullptr;         // [rows][64] float32
+  void* idb = nullptr;          // [rows][80] float32/float64
+  void* texb = nullptr;         // [rows][80]
+  void* meanshape = nullptr;    // [rows]
+  void* meantex = nullptr;      // [rows]
+  bool idb64 = false, texb64 = false, mean64 = false, meantex64 = false;
+  int4* tri = nullptr;          // [ntri] internal vertex ids + original triangle index
+  int* v_int2orig_dev = nullptr;
+  // device: vertex tiles
+  int ntiles = 0;
+  vp::TileDesc* tiles = nullptr;
+  uint32_t* ltri = nullptr;
+  int* halo = nullptr;
+  uint16_t* ring = nullptr;     // [nver][8] local triangle index per point_buf slot
+  // device: per-clip state
+  double* base = nullptr;       // [nver][3]
+  float* tex = nullptr;         // [nver][3]
+  float* coeff_tmp = nullptr;   // [160] staging for id/tex coefficients
+  bool have_base = false, have_tex = false;
+
+  // workspaces (grow only)
+  vp::DevBuf ws_ex, ws_params, ws_disp, ws_vrec, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+
+  // profiling
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  float prof_ms[8] = {0};
+
+  std::mutex mu;
+};
+
+namespace vp {
+
+// ---- reconstruction (reconstruct.cu) ----------------------------------------------------
+int launch_identity(vp_model* m, const float* id_dev, const float* tex_dev, cudaStream_t st);
+int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st);
+// disp_dev may be NULL (no expression displacement).  vrec_dev may be NULL (no raster records).
+int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes,
+                  int rotate_first, double focal, double center, double raster_scale, float4* vrec_dev,
+                  const ReconOut& out, cudaStream_t st);
+
+}  // namespace vp

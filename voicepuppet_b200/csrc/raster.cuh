@@ -1,0 +1,269 @@
+// Z-buffer rasterizer kernels (K3 scatter + K4 resolve), order independent.
+//
+// The reference walks triangles sequentially and keeps a pixel when "d > depth[p]"
+// (utils/cython/mesh_core.cpp:153,211).  That fixed point is: the largest candidate depth
+// strictly above the caller's initial depth, ties to the lowest triangle index.  We get it
+// with one 64-bit atomicMax per (triangle, pixel) candidate on key = (depth code, ~index)
+// (vp_math.cuh), then a resolve pass that recomputes the winner's outputs with the same
+// float32 expressions -- so image/mask/depth/triangle/weights are bit-identical.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "vp_math.cuh"
+
+namespace vp {
+
+constexpr int kRasterBlock = 256;
+constexpr int kSmallBox = 8;  // boxes up to this many pixels are walked by the owning lane
+
+enum RasterMode { kModeColors = 0, kModeTriangles = 1 };
+
+// ---- vertex / triangle fetch policies -------------------------------------------------
+// Generic: the reference's flat arrays (float xyz per vertex, int32 index triples).
+struct GenericMesh {
+  const float* vertices;   // [frames][3*nver]
+  const int* triangles;    // [3*ntri]
+  size_t frame_stride;     // floats
+  __device__ __forceinline__ void indices(int f, int& a, int& b, int& c, uint32_t& id) const {
+    a = __ldg(triangles + 3 * (size_t)f);
+    b = __ldg(triangles + 3 * (size_t)f + 1);
+    c = __ldg(triangles + 3 * (size_t)f + 2);
+    id = (uint32_t)f;
+  }
+  __device__ __forceinline__ void vertex(int frame, int i, float& x, float& y, float& z, uint32_t& rgba) const {
+    const float* p = vertices + (size_t)frame * frame_stride + 3 * (size_t)i;
+    x = __ldg(p);
+    y = __ldg(p + 1);
+    z = __ldg(p + 2);
+    rgba = 0;
+  }
+};
+
+// Packed: the fused pipeline's records.  Vertex = float4 (x, y, z, rgba bits), triangle =
+// int4 (internal vertex ids, original triangle index for the tie-break).
+struct PackedMesh {
+  const float4* vertices;  // [frames][nver_pad]
+  const int4* triangles;   // [ntri]
+  size_t frame_stride;     // float4 elements
+  __device__ __forceinline__ void indices(int f, int& a, int& b, int& c, uint32_t& id) const {
+    const int4 t = __ldg(triangles + f);
+    a = t.x;
+    b = t.y;
+    c = t.z;
+    id = (uint32_t)t.w;
+  }
+  __device__ __forceinline__ void vertex(int frame, int i, float& x, float& y, float& z, uint32_t& rgba) const {
+    const float4 v = __ldg(vertices + (size_t)frame * frame_stride + i);
+    x = v.x;
+    y = v.y;
+    z = v.z;
+    rgba = __float_as_uint(v.w);
+  }
+};
+
+struct Candidate {  // what one lane knows about its triangle
+  TriSetup s;
+  float z0, z1, z2;  // kModeTriangles: per-corner depth; kModeColors: z0 = flat depth
+  uint32_t id;
+  int n;             // bbox pixel count (0 = nothing to do)
+};
+
+template <int MODE>
+__device__ __forceinline__ void offer_pixel(const Candidate& c, int j, unsigned long long* keys, int h, int w) {
+  const int bw = c.s.x_hi - c.s.x_lo + 1;
+  const int y = c.s.y_lo + j / bw;
+  const int x = c.s.x_lo + j % bw;
+  float u, v;
+  pixel_uv(c.s, x, y, u, v);
+  if (MODE == kModeColors) {
+    if (uv_inside(u, v)) atomicMax(keys + (size_t)y * w + x, make_key(c.z0, c.id));
+  } else {
+    if (in_border(x, y, h, w) || uv_inside(u, v)) {
+      float w0, w1, w2;
+      const float d = weights_depth(u, v, c.z0, c.z1, c.z2, w0, w1, w2);
+      if (d == d) atomicMax(keys + (size_t)y * w + x, make_key(d, c.id));
+    }
+  }
+}
+
+// One lane per triangle; boxes larger than kSmallBox are walked by the whole warp.
+// tri_color (may be NULL, kModeColors + PackedMesh only): flat colour per ORIGINAL triangle
+// index, written here so that the resolve pass needs one gather per pixel.
+// const_init: keys start at 0 and the initial depth is the constant kInitDepth, so the
+// strict "d > initial" test is done here per triangle instead of through init keys.
+template <int MODE, typename Mesh>
+__global__ void __launch_bounds__(kRasterBlock)
+raster_scatter_kernel(Mesh mesh, unsigned long long* __restrict__ keys, uint32_t* __restrict__ tri_color,
+                      int ntri, int h, int w, int const_init) {
+  const int frame = blockIdx.y;
+  const int f = blockIdx.x * kRasterBlock + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  keys += (size_t)frame * h * w;
+
+  Candidate c;
+  c.n = 0;
+  c.id = 0;
+  c.z0 = c.z1 = c.z2 = 0.f;
+  if (f < ntri) {
+    int ia, ib, ic;
+    mesh.indices(f, ia, ib, ic, c.id);
+    float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+    uint32_t r0, r1, r2;
+    mesh.vertex(frame, ia, x0, y0, z0, r0);
+    mesh.vertex(frame, ib, x1, y1, z1, r1);
+    mesh.vertex(frame, ic, x2, y2, z2, r2);
+    if (tri_bbox(c.s, x0, y0, x1, y1, x2, y2, h, w)) {
+      tri_edges(c.s, x0, y0, x1, y1, x2, y2);
+      c.n = (c.s.x_hi - c.s.x_lo + 1) * (c.s.y_hi - c.s.y_lo + 1);
+      if (MODE == kModeColors) {
+        const float d = flat_depth(z0, z1, z2);
+        c.z0 = d;
+        if (!(d == d)) c.n = 0;                          // NaN never wins a '>' test
+        if (const_init && !(d > kInitDepth)) c.n = 0;    // mesh_core.cpp:211 against -99999
+        if (tri_color != nullptr && c.n > 0) {
+          // integral colours in [0,255] packed by the vertex kernel: sum <= 765 is exact in float,
+          // so integer arithmetic equals mesh_core.cpp:219
+          const uint32_t r = ((r0 & 255u) + (r1 & 255u) + (r2 & 255u)) / 3u;
+          const uint32_t g = (((r0 >> 8) & 255u) + ((r1 >> 8) & 255u) + ((r2 >> 8) & 255u)) / 3u;
+          const uint32_t b = (((r0 >> 16) & 255u) + ((r1 >> 16) & 255u) + ((r2 >> 16) & 255u)) / 3u;
+          tri_color[(size_t)frame * ntri + c.id] = r | (g << 8) | (b << 16) | 0xFF000000u;
+        }
+      } else {
+        c.z0 = z0;
+        c.z1 = z1;
+        c.z2 = z2;
+      }
+    }
+  }
+
+  if (c.n > 0 && c.n <= kSmallBox) {
+    for (int j = 0; j < c.n; ++j) offer_pixel<MODE>(c, j, keys, h, w);
+  }
+  unsigned big = __ballot_sync(0xFFFFFFFFu, c.n > kSmallBox);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    Candidate o;
+    o.s.ax = __shfl_sync(0xFFFFFFFFu, c.s.ax, src);
+    o.s.ay = __shfl_sync(0xFFFFFFFFu, c.s.ay, src);
+    o.s.e0x = __shfl_sync(0xFFFFFFFFu, c.s.e0x, src);
+    o.s.e0y = __shfl_sync(0xFFFFFFFFu, c.s.e0y, src);
+    o.s.e1x = __shfl_sync(0xFFFFFFFFu, c.s.e1x, src);
+    o.s.e1y = __shfl_sync(0xFFFFFFFFu, c.s.e1y, src);
+    o.s.d00 = __shfl_sync(0xFFFFFFFFu, c.s.d00, src);
+    o.s.d01 = __shfl_sync(0xFFFFFFFFu, c.s.d01, src);
+    o.s.d11 = __shfl_sync(0xFFFFFFFFu, c.s.d11, src);
+    o.s.inv = __shfl_sync(0xFFFFFFFFu, c.s.inv, src);
+    o.s.x_lo = __shfl_sync(0xFFFFFFFFu, c.s.x_lo, src);
+    o.s.x_hi = __shfl_sync(0xFFFFFFFFu, c.s.x_hi, src);
+    o.s.y_lo = __shfl_sync(0xFFFFFFFFu, c.s.y_lo, src);
+    o.s.y_hi = __shfl_sync(0xFFFFFFFFu, c.s.y_hi, src);
+    o.z0 = __shfl_sync(0xFFFFFFFFu, c.z0, src);
+    if (MODE == kModeTriangles) {
+      o.z1 = __shfl_sync(0xFFFFFFFFu, c.z1, src);
+      o.z2 = __shfl_sync(0xFFFFFFFFu, c.z2, src);
+    } else {
+      o.z1 = o.z2 = 0.f;
+    }
+    o.id = __shfl_sync(0xFFFFFFFFu, c.id, src);
+    o.n = __shfl_sync(0xFFFFFFFFu, c.n, src);
+    for (int j = lane; j < o.n; j += 32) offer_pixel<MODE>(o, j, keys, h, w);
+  }
+}
+
+// keys[p] = init_key(depth[p]) for the caller-initialised depth buffer.
+__global__ void keys_from_depth_kernel(const float* __restrict__ depth, unsigned long long* __restrict__ keys,
+                                       size_t n) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) keys[p] = init_key(depth[p]);
+}
+
+// Generic resolve for render_colors_core: any channel count, float colours, in-place buffers.
+__global__ void resolve_colors_generic_kernel(const unsigned long long* __restrict__ keys, GenericMesh mesh,
+                                              const float* __restrict__ colors, size_t color_stride,
+                                              unsigned char* __restrict__ image, unsigned char* __restrict__ mask,
+                                              float* __restrict__ depth, int* __restrict__ tri_out, int h, int w,
+                                              int c) {
+  const int frame = blockIdx.y;
+  const size_t npix = (size_t)h * w;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const size_t gp = (size_t)frame * npix + p;
+  const int t = key_triangle(keys[gp]);
+  if (tri_out) tri_out[gp] = t;
+  if (t < 0) return;
+  int ia, ib, ic;
+  uint32_t id;
+  mesh.indices(t, ia, ib, ic, id);
+  const float* vb = mesh.vertices + (size_t)frame * mesh.frame_stride;
+  depth[gp] = flat_depth(vb[3 * (size_t)ia + 2], vb[3 * (size_t)ib + 2], vb[3 * (size_t)ic + 2]);
+  mask[gp] = 255;
+  const float* cb = colors + (size_t)frame * color_stride;
+  for (int k = 0; k < c; ++k)
+    image[gp * c + k] = flat_color(cb[(size_t)c * ia + k], cb[(size_t)c * ib + k], cb[(size_t)c * ic + k]);
+}
+
+// Resolve for rasterize_triangles_core: recompute the winner's weights and depth.
+__global__ void resolve_triangles_kernel(const unsigned long long* __restrict__ keys, GenericMesh mesh,
+                                         float* __restrict__ depth, int* __restrict__ tri_buf,
+                                         float* __restrict__ weights, int h, int w) {
+  const size_t npix = (size_t)h * w;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int t = key_triangle(keys[p]);
+  if (t < 0) return;
+  int ia, ib, ic;
+  uint32_t id;
+  mesh.indices(t, ia, ib, ic, id);
+  float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+  uint32_t r;
+  mesh.vertex(0, ia, x0, y0, z0, r);
+  mesh.vertex(0, ib, x1, y1, z1, r);
+  mesh.vertex(0, ic, x2, y2, z2, r);
+  TriSetup s;
+  tri_edges(s, x0, y0, x1, y1, x2, y2);
+  float u, v, w0, w1, w2;
+  pixel_uv(s, (int)(p % w), (int)(p / w), u, v);
+  depth[p] = weights_depth(u, v, z0, z1, z2, w0, w1, w2);
+  tri_buf[p] = t;
+  weights[3 * p + 0] = w0;
+  weights[3 * p + 1] = w1;
+  weights[3 * p + 2] = w2;
+}
+
+// Fused-path resolve: 4 pixels per thread, one tri_color gather per covered pixel, every pixel
+// written (uncovered -> 0), so the image needs no clear.  Requires (h*w) % 4 == 0.
+__global__ void __launch_bounds__(256)
+resolve_packed_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ tri_color,
+                      unsigned char* __restrict__ image, unsigned char* __restrict__ mask, int ntri,
+                      size_t npix) {
+  const int frame = blockIdx.y;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
+  if (q * 4 >= npix) return;
+  const size_t base = (size_t)frame * npix + q * 4;
+  const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(keys + base);
+  const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(keys + base + 2);
+  const unsigned long long k[4] = {k01.x, k01.y, k23.x, k23.y};
+  const uint32_t* tc = tri_color + (size_t)frame * ntri;
+  uint32_t col[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = key_triangle(k[i]);
+    col[i] = (t >= 0) ? __ldg(tc + t) : 0u;
+  }
+  // 12 bytes of RGB for 4 pixels as three 32-bit words
+  const uint32_t w0 = (col[0] & 0xFFFFFFu) | ((col[1] & 0xFFu) << 24);
+  const uint32_t w1 = ((col[1] >> 8) & 0xFFFFu) | ((col[2] & 0xFFFFu) << 16);
+  const uint32_t w2 = ((col[2] >> 16) & 0xFFu) | ((col[3] & 0xFFFFFFu) << 8);
+  uint32_t* out = reinterpret_cast<uint32_t*>(image + base * 3);
+  out[0] = w0;
+  out[1] = w1;
+  out[2] = w2;
+  if (mask != nullptr) {
+    const uint32_t m = (col[0] >> 24) | ((col[1] >> 24) << 8) | ((col[2] >> 24) << 16) | ((col[3] >> 24) << 24);
+    *reinterpret_cast<uint32_t*>(mask + base) = m;
+  }
+}
+
+}  // namespace vp

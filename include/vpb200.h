@@ -55,6 +55,12 @@ int vp_version(void);
 /* number of visible CUDA devices, or a negative VP_ERR code */
 int vp_device_count(void);
 
+/* Page-locked host memory for the host-pointer entry points: copies from/to such buffers are
+ * truly asynchronous, so vp_render_sequence can overlap the device->host drain of one chunk
+ * with the rendering of the next.  Pageable memory works too (slower). */
+int vp_host_alloc(void** out, size_t bytes);
+int vp_host_free(void* p);
+
 /* ---------------------------------------------------------------------------------------
  * mesh_core_cython replacements: caller-initialised buffers, mutated in place.
  * --------------------------------------------------------------------------------------- */
@@ -99,6 +105,23 @@ int vp_model_create(vp_model** out, int device, int nver, int ntri, const void* 
 void vp_model_destroy(vp_model* m);
 int vp_model_nver(const vp_model* m);
 int vp_model_ntri(const vp_model* m);
+int vp_model_ntiles(const vp_model* m);
+
+/* Host-only introspection of the one-off mesh analysis vp_model_create performs (no CUDA
+ * device needed): vertices renumbered along a Morton curve, triangles renumbered for the
+ * rasterizer, vertex tiles with tile-local adjacency.  Used by the CPU test-suite to check the
+ * tables against Compute_norm (reconstruct_mesh.py:35-52).
+ *   tri[ntri][3], point_buf[nver][8] 0-based (pad = anything outside [0, ntri)), xyz[nver][3].
+ * vp_topology_copy: v_int2orig[nver], tri_int[ntri][4] (internal a,b,c + original index),
+ *   tiles[ntiles][6] (v_begin, nv, nlv, nlt, halo_off, ltri_off), ltri[nltri] (3 x 10-bit local
+ *   vertex ids), halo[nhalo] (internal vertex ids), ring[nver][8] (local triangle id, 0xFFFF pad). */
+typedef struct vp_topology vp_topology;
+int vp_topology_build(vp_topology** out, int nver, int ntri, const int* tri, const int* point_buf,
+                      const double* xyz);
+void vp_topology_destroy(vp_topology* t);
+int vp_topology_sizes(const vp_topology* t, int* ntiles, int* nltri, int* nhalo);
+int vp_topology_copy(const vp_topology* t, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
+                     int* halo, uint16_t* ring);
 
 /* Per-clip constants ("identity mean precomputed once"): base shape = meanshape + idBase.id
  * - center, texture = meantex + texBase.tex.  Either pointer may be NULL to keep the old one. */
@@ -150,6 +173,12 @@ int vp_reconstruct(vp_model* m, const vp_frames* frames, const vp_recon_out* out
 int vp_illumination(int device, int n, const double* texture, const double* norm, const float* gamma,
                     double* color, double* lighting);
 
+/* Projection_layer on a caller-supplied shape (reconstruct_mesh.py:100-120), float64:
+ * shape[n][3], rotation9 row-major 3x3, translation3 -> projection[n][2] (not flipped), z_buffer[n]. */
+int vp_projection(int device, int n, const double* shape, const double* rotation9,
+                  const float* translation3, double focal, double center, double* projection,
+                  double* z_buffer);
+
 /* The whole hot path, coefficients -> rendered frames (infer_bfmvid.py:91-109 per frame):
  * reconstruction, colours clipped to [0,255] and truncated, vertices (x, S - y, -z) scaled by
  * res/224, flat-shaded z-buffer rasterization at h = w = res.
@@ -174,8 +203,9 @@ int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev,
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 unsigned long long vp_launch_count(void);
 
-/* Per-kernel device time of the last vp_render_sequence_dev call when profiling is enabled
- * (CUDA events around each kernel, accumulated over chunks).  names: semicolon separated. */
+/* Per-kernel device time of the last vp_render_sequence(_dev) call when profiling is enabled
+ * (CUDA events around each kernel, accumulated over chunks; enabling it makes the _dev variant
+ * synchronise).  Four slots: names "basis;vertex;scatter;resolve" (semicolon separated). */
 int vp_set_profiling(vp_model* m, int enabled);
 int vp_get_profile(vp_model* m, char* names, int names_cap, float* ms, int ms_cap);
 

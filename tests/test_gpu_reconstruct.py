@@ -1,0 +1,113 @@
+"""GPU parity, reconstruction: the drop-in reconstruct_mesh (CUDA, through the C ABI) against the
+numpy oracle (pinned to the live reference) and the golden outputs of the reference itself.
+Tolerance (BASELINE.json north_star): 1e-5 relative to each array's scale.
+Reference: utils/reconstruct_mesh.py:5-223."""
+import numpy as np
+import pytest
+
+from oracle import reconstruct_oracle as orc
+from voicepuppet_b200 import reconstruct_mesh as rm, synthetic
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+NAMES7 = ('shape', 'texture', 'color', 'projection', 'zbuffer', 'landmarks', 'translation')
+
+
+def rel_err(a, b):
+  a = np.asarray(a, dtype=np.float64)
+  b = np.asarray(b, dtype=np.float64)
+  assert a.shape == b.shape, (a.shape, b.shape)
+  return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+def test_small_model_against_reference_golden(golden_small, small_model):
+  g = golden_small
+  for t in range(4):
+    c = g['coeffs'][t:t + 1]
+    out = rm.Reconstruction(c, small_model)
+    assert len(out) == 7
+    for name, arr in zip(NAMES7, out):
+      ref = g['rec%d_%s' % (t, name)]
+      assert arr.shape == ref.shape and arr.dtype == ref.dtype, name
+      assert rel_err(arr, ref) <= REL, (name, rel_err(arr, ref))
+    out = rm.Reconstruction_rotation(c, small_model, g['jitter'][t])
+    assert len(out) == 6
+    for name, arr in zip(NAMES7[:6], out):
+      ref = g['rot%d_%s' % (t, name)]
+      assert arr.shape == ref.shape and arr.dtype == ref.dtype, name
+      assert rel_err(arr, ref) <= REL, (name, rel_err(arr, ref))
+
+
+def test_stage_functions_against_reference_golden(golden_small, small_model):
+  g = golden_small
+  c = g['coeffs'][0:1]
+  idc, exc, texc, ang, gam, trans = rm.Split_coeff(c)
+  sh = rm.Shape_formation(idc, exc, small_model)
+  want = orc.shape_formation(idc, exc, small_model)
+  assert sh.dtype == want.dtype and rel_err(sh, want) <= REL
+  tex = rm.Texture_formation(texc, small_model)
+  want_tex = orc.texture_formation(texc, small_model)
+  assert tex.dtype == want_tex.dtype and rel_err(tex, want_tex) <= REL
+  nrm = rm.Compute_norm(want, small_model)
+  assert nrm.dtype == np.float64 and rel_err(nrm, g['stage_norm']) <= REL
+  rot = rm.Compute_rotation_matrix(ang)
+  assert np.array_equal(rot, g['stage_rotation'])
+  pr, zb = rm.Projection_layer(want, rot, trans)
+  assert rel_err(pr, g['stage_projection']) <= REL and rel_err(zb, g['stage_zbuffer']) <= REL
+  col, lit = rm.Illumination_layer(want_tex, nrm, gam)
+  wcol, wlit = orc.illumination_layer(want_tex, g['stage_norm'], gam)
+  assert rel_err(col, wcol) <= REL and rel_err(lit, wlit) <= REL
+
+
+@pytest.mark.parametrize('ex_dtype', [np.float64, np.float32])
+def test_full_model_against_oracle(full_model, ex_dtype):
+  model = full_model if ex_dtype == np.float64 else synthetic.cached_model(ex_dtype=np.float32)
+  coeffs = synthetic.make_coeffs(30, seed=1)
+  jit = orc.jitter_angle_sequence(30)
+  for t in (0, 29):
+    got = rm.Reconstruction_rotation(coeffs[t:t + 1], model, jit[t])
+    want = orc.reconstruction_rotation(coeffs[t:t + 1], model, jit[t])
+    for name, a, b in zip(NAMES7[:6], got, want):
+      assert a.dtype == b.dtype, name
+      assert rel_err(a, b) <= REL, (name, rel_err(a, b))
+    # the projected vertices are much better than the contract: a few 1e-6 pixels
+    assert np.max(np.abs(got[3] - want[3])) < 2e-5
+  got = rm.Reconstruction(coeffs[3:4], model)
+  want = orc.reconstruction(coeffs[3:4], model)
+  for name, a, b in zip(NAMES7, got, want):
+    assert a.dtype == b.dtype and rel_err(a, b) <= REL, name
+
+
+def test_full_model_against_reference_golden(golden_full, full_model):
+  g = golden_full
+  coeffs = synthetic.make_coeffs(30, seed=1)
+  jit = orc.jitter_angle_sequence(30)
+  for t, res in zip(g['frames'], g['resolutions']):
+    out = rm.Reconstruction_rotation(coeffs[t:t + 1], full_model, jit[t])
+    key = 'f%d_r%d_' % (t, res)
+    for name, arr in zip(NAMES7[:6], out):
+      sub = arr if name == 'landmarks' else arr[:, ::int(g['stride'])]
+      assert rel_err(sub, g[key + name]) <= REL, name
+
+
+def test_identity_rotation_shape(small_model, golden_small):
+  # SURVEY 8c identity 3: Reconstruction_rotation(...)[0] == Shape_formation(...) @ R(angles)
+  c = golden_small['coeffs'][1:2]
+  a = golden_small['jitter'][1]
+  shape = rm.Reconstruction_rotation(c, small_model, a)[0]
+  want = np.matmul(rm.Shape_formation(c[:, :80], c[:, 80:144], small_model).astype(np.float64),
+                   rm.Compute_rotation_matrix(a))
+  assert rel_err(shape, want) <= 1e-12
+
+
+def test_linearity_of_the_expression_basis(full_model):
+  """Size-independent property: shape(ex1 + ex2) - shape(0) == (shape(ex1) - shape(0)) + (shape(ex2) - shape(0))."""
+  c = synthetic.make_coeffs(3, seed=4)
+  idc = c[0:1, :80]
+  z = np.zeros((1, 64), np.float32)
+  s0 = rm.Shape_formation(idc, z, full_model).astype(np.float64)
+  s1 = rm.Shape_formation(idc, c[1:2, 80:144], full_model) - s0
+  s2 = rm.Shape_formation(idc, c[2:3, 80:144], full_model) - s0
+  s12 = rm.Shape_formation(idc, c[1:2, 80:144] + c[2:3, 80:144], full_model) - s0
+  assert np.max(np.abs(s12 - (s1 + s2))) < 2e-7

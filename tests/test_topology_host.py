@@ -1,0 +1,122 @@
+"""Host logic of vp_model_create: the vertex tiles (voicepuppet_b200/csrc/topology.cu) must encode
+exactly the adjacency Compute_norm walks (reference utils/reconstruct_mesh.py:35-52).  The tables
+are pulled through the C ABI (no GPU needed) and the vertex kernel's normal computation is
+re-enacted from them in numpy, then compared with the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import reconstruct_oracle as orc
+from voicepuppet_b200 import _lib, synthetic
+
+TILE_V, TILE_LV, TILE_LT = 128, 384, 512
+
+
+def build(model):
+  lib = _lib.lib()
+  nver = model.meanshape.size // 3
+  tri = np.ascontiguousarray((model.tri - 1).astype(np.int32))
+  pb = np.ascontiguousarray((model.point_buf - 1).astype(np.int32))
+  xyz = np.ascontiguousarray(model.meanshape.reshape(-1, 3).astype(np.float64))
+  h = ctypes.c_void_p()
+  _lib.check(lib.vp_topology_build(ctypes.byref(h), nver, tri.shape[0], _lib.ptr(tri), _lib.ptr(pb), _lib.ptr(xyz)))
+  nt, nl, nh = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+  _lib.check(lib.vp_topology_sizes(h, ctypes.byref(nt), ctypes.byref(nl), ctypes.byref(nh)))
+  t = dict(v_int2orig=np.zeros(nver, np.int32), tri_int=np.zeros((tri.shape[0], 4), np.int32),
+           tiles=np.zeros((nt.value, 6), np.int32), ltri=np.zeros(nl.value, np.uint32),
+           halo=np.zeros(nh.value, np.int32), ring=np.zeros((nver, 8), np.uint16))
+  _lib.check(lib.vp_topology_copy(h, *[_lib.ptr(t[k]) for k in ('v_int2orig', 'tri_int', 'tiles', 'ltri', 'halo', 'ring')]))
+  lib.vp_topology_destroy(h)
+  return t, tri, pb
+
+
+def normals_from_tiles(t, shape_orig):
+  """What vertex_tile_kernel does for the normals, in float64."""
+  nver = shape_orig.shape[0]
+  shape_int = shape_orig[t['v_int2orig']]
+  out = np.zeros((nver, 3))
+  for v_begin, nv, nlv, nlt, halo_off, ltri_off in t['tiles']:
+    local = np.concatenate([np.arange(v_begin, v_begin + nv), t['halo'][halo_off:halo_off + nlv - nv]])
+    pos = shape_int[local]
+    lt = t['ltri'][ltri_off:ltri_off + nlt]
+    a, b, c = lt & 1023, (lt >> 10) & 1023, (lt >> 20) & 1023
+    fn = np.cross(pos[a] - pos[b], pos[b] - pos[c]) if nlt else np.zeros((0, 3))
+    fn = np.concatenate([fn, np.zeros((1, 3))])
+    ring = t['ring'][v_begin:v_begin + nv].astype(np.int64)
+    ring[ring == 0xFFFF] = nlt
+    acc = np.zeros((nv, 3))
+    for s in range(8):
+      acc = acc + fn[ring[:, s]]
+    with np.errstate(invalid='ignore', divide='ignore'):
+      out[t['v_int2orig'][v_begin:v_begin + nv]] = acc / np.linalg.norm(acc, axis=1, keepdims=True)
+  return out
+
+
+def check_model(model):
+  t, tri, pb = build(model)
+  nver, ntri = model.meanshape.size // 3, tri.shape[0]
+  # permutations
+  assert sorted(t['v_int2orig'].tolist()) == list(range(nver))
+  assert sorted(t['tri_int'][:, 3].tolist()) == list(range(ntri))
+  o2i = np.empty(nver, np.int64)
+  o2i[t['v_int2orig']] = np.arange(nver)
+  assert np.array_equal(t['tri_int'][:, :3], o2i[tri[t['tri_int'][:, 3]]])     # corner order preserved
+  # tiles partition the vertices and respect the kernel's shared-memory limits
+  tiles = t['tiles']
+  assert tiles[0, 0] == 0 and np.array_equal(tiles[1:, 0], np.cumsum(tiles[:-1, 1])) and tiles[:, 1].sum() == nver
+  assert tiles[:, 1].max() <= TILE_V and tiles[:, 2].max() <= TILE_LV and tiles[:, 3].max() <= TILE_LT
+  assert np.all(tiles[:, 2] >= tiles[:, 1])
+  # the normals computed from the tables equal Compute_norm
+  coeff = synthetic.make_coeffs(1, seed=5)
+  shape = orc.shape_formation(coeff[:, :80], coeff[:, 80:144], model)
+  want = orc.compute_norm(shape, model)[0]
+  got = normals_from_tiles(t, shape[0].astype(np.float64))
+  both_nan = np.isnan(want) & np.isnan(got)
+  assert np.allclose(np.where(both_nan, 0, got), np.where(both_nan, 0, want), rtol=0, atol=1e-12)
+  return t
+
+
+def test_small_model(small_model):
+  check_model(small_model)
+
+
+def test_full_model_tiles(full_model):
+  t = check_model(full_model)
+  tiles = t['tiles']
+  # spatial order works: tiles are nearly full and the halo stays small
+  assert tiles.shape[0] <= 300
+  assert tiles[:, 2].mean() < 260
+
+
+def test_awkward_meshes():
+  """Isolated vertices, valence-8 fans, pad slots in the middle of a ring, duplicate ring entries."""
+  rng = np.random.Generator(np.random.PCG64(3))
+  nver, ntri = 700, 1500
+  tri = rng.integers(0, nver - 20, (ntri, 3))            # last 20 vertices are isolated
+  pb = np.full((nver, 8), ntri, dtype=np.int64)
+  fill = np.zeros(nver, dtype=np.int64)
+  for f in range(ntri):
+    for v in tri[f]:
+      if fill[v] < 8:
+        pb[v, fill[v]] = f
+        fill[v] += 1
+  pb[5, 0], pb[5, 3] = ntri, pb[5, 0]                     # pad slot first
+  pb[6, 1] = pb[6, 0]                                     # duplicate face
+  pts = rng.random((nver, 3))
+  model = synthetic.SyntheticBFM(
+      meanshape=pts.reshape(1, -1).astype(np.float64), idBase=np.zeros((3 * nver, 80), np.float32),
+      exBase=np.zeros((3 * nver, 64), np.float32), meantex=np.zeros((1, 3 * nver), np.float32),
+      texBase=np.zeros((3 * nver, 80), np.float32), point_buf=(pb + 1).astype(np.float64),
+      tri=(tri + 1).astype(np.float64), keypoints=np.arange(68, dtype=np.int32))
+  check_model(model)
+
+
+def test_rejects_bad_indices():
+  lib = _lib.lib()
+  tri = np.array([[0, 1, 7]], np.int32)
+  pb = np.zeros((3, 8), np.int32)
+  xyz = np.zeros((3, 3))
+  h = ctypes.c_void_p()
+  rc = lib.vp_topology_build(ctypes.byref(h), 3, 1, _lib.ptr(tri), _lib.ptr(pb), _lib.ptr(xyz))
+  assert rc != 0 and b'out of range' in lib.vp_last_error()

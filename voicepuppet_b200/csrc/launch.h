@@ -19,13 +19,13 @@ int launch_scatter_generic(int mode, const float* vertices, size_t frame_stride,
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
                           unsigned long long* keys, uint32_t* tri_color, int nframes, int ntri, int h, int w,
                           cudaStream_t st);
-int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, unsigned char* image,
+int launch_resolve_packed(unsigned long long* keys, const uint32_t* tri_color, unsigned char* image,
                           unsigned char* mask, int nframes, int ntri, int h, int w, cudaStream_t st);
 
-// ---- vertex-tile topology (model.cu builds it, reconstruct.cu consumes it) -------------
-constexpr int kTileV = 128;    // own vertices per tile == threads per CTA of the vertex kernel
-constexpr int kTileLV = 384;   // own + halo vertices
-constexpr int kTileLT = 512;   // triangles touching the tile's own vertices
+// ---- vertex-tile topology (topology.cpp builds it, reconstruct.cu consumes it) ----------
+constexpr int kTileV = 128;    // max own vertices per tile == threads per CTA of the vertex kernel
+constexpr int kTileLV = 384;   // max own + halo vertices
+constexpr int kTileLT = 512;   // max triangles touching the tile's own vertices
 constexpr uint16_t kRingPad = 0xFFFF;
 
 struct TileDesc {
@@ -37,6 +37,21 @@ struct TileDesc {
   int ltri_off;  // into ltri[] (3 x 10-bit local vertex indices)
 };
 
+// Host-side result of the one-off mesh analysis (topology.cpp).
+struct Topology {
+  int nver = 0, ntri = 0;
+  std::vector<int> v_int2orig, v_orig2int;
+  std::vector<int> tri_int;        // [ntri][4]: internal vertex ids a,b,c + ORIGINAL triangle index
+  std::vector<TileDesc> tiles;
+  std::vector<uint32_t> ltri;
+  std::vector<int> halo;
+  std::vector<uint16_t> ring;      // [nver][8] in internal vertex order
+};
+
+// tri: [ntri][3] 0-based original vertex ids; point_buf: [nver][8] 0-based original triangle ids
+// (anything outside [0, ntri) is a pad slot); xyz: [nver][3] mean shape used for the spatial order.
+int build_topology(Topology& out, int nver, int ntri, const int* tri, const int* point_buf, const double* xyz);
+
 // Optional per-vertex outputs of the vertex kernel, in the MODEL's (original) vertex order.
 struct ReconOut {
   double* shape = nullptr;   // [T][nver][3]
@@ -45,7 +60,6 @@ struct ReconOut {
   double* proj = nullptr;    // [T][nver][2]
   double* zbuf = nullptr;    // [T][nver]
   int flip_y = 1;
-  double image_size = 224.0;
 };
 
 }  // namespace vp
@@ -55,20 +69,19 @@ struct vp_model {
   int device = 0;
   int nver = 0, ntri = 0;
   int rows = 0;         // 3 * nver
-  int row_stride = 0;   // floats per frame in the displacement buffer (rows rounded up to 32)
+  int rows_pad = 0;     // rows rounded up to 128: row count of exb and floats per frame in disp
   int vrec_stride = 0;  // float4 per frame in the vertex-record buffer
   double center[3] = {0, 0, 0};
 
-  // host-side permutations (internal order is a Morton order of the mean shape)
-  std::vector<int> v_int2orig, v_orig2int, t_int2orig;
+  vp::Topology topo;    // host copy (permutations are needed by the setters/getters)
 
-  // device: model (internal vertex order)
-  float* exb = nullptr;         // [rows][64] float32
+  // device: model (internal vertex order; row = 3 * internal vertex + axis)
+  float* exb = nullptr;         // [rows_pad][64] float32
   void* idb = nullptr;          // [rows][80] float32/float64
   void* texb = nullptr;         // [rows][80]
-  void* meanshape = nullptr;    // [rows]
-  void* meantex = nullptr;      // [rows]
-  bool idb64 = false, texb64 = false, mean64 = false, meantex64 = false;
+  double* meanshape = nullptr;  // [rows]
+  double* meantex = nullptr;    // [rows]
+  bool idb64 = false, texb64 = false;
   int4* tri = nullptr;          // [ntri] internal vertex ids + original triangle index
   int* v_int2orig_dev = nullptr;
   // device: vertex tiles
@@ -85,12 +98,12 @@ struct vp_model {
 
   // workspaces (grow only)
   vp::DevBuf ws_ex, ws_params, ws_disp, ws_vrec, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
+  size_t keys_clean_bytes = 0;  // prefix of ws_keys known to be all-zero
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 
   // profiling
   bool profiling = false;
-  std::vector<cudaEvent_t> prof_events;
   float prof_ms[8] = {0};
 
   std::mutex mu;
@@ -98,12 +111,14 @@ struct vp_model {
 
 namespace vp {
 
+enum ProfSlot { kProfBasis = 0, kProfVertex = 1, kProfScatter = 2, kProfResolve = 3, kProfSlots = 4 };
+
 // ---- reconstruction (reconstruct.cu) ----------------------------------------------------
 int launch_identity(vp_model* m, const float* id_dev, const float* tex_dev, cudaStream_t st);
 int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st);
 // disp_dev may be NULL (no expression displacement).  vrec_dev may be NULL (no raster records).
 int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes,
-                  int rotate_first, double focal, double center, double raster_scale, float4* vrec_dev,
-                  const ReconOut& out, cudaStream_t st);
+                  int rotate_first, double focal, double center, double image_size, double raster_scale,
+                  float4* vrec_dev, const ReconOut& out, cudaStream_t st);
 
 }  // namespace vp

@@ -54,7 +54,7 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
   return VP_OK;
 }
 
-int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, unsigned char* image,
+int launch_resolve_packed(unsigned long long* keys, const uint32_t* tri_color, unsigned char* image,
                           unsigned char* mask, int nframes, int ntri, int h, int w, cudaStream_t st) {
   const size_t npix = (size_t)h * w;
   if (nframes == 0 || npix == 0) return VP_OK;

@@ -233,9 +233,10 @@ __global__ void resolve_triangles_kernel(const unsigned long long* __restrict__ 
 }
 
 // Fused-path resolve: 4 pixels per thread, one tri_color gather per covered pixel, every pixel
-// written (uncovered -> 0), so the image needs no clear.  Requires (h*w) % 4 == 0.
+// written (uncovered -> 0), so the image needs no clear.  The consumed keys are zeroed in the
+// same pass, which is what the next chunk's scatter expects.  Requires (h*w) % 4 == 0.
 __global__ void __launch_bounds__(256)
-resolve_packed_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ tri_color,
+resolve_packed_kernel(unsigned long long* __restrict__ keys, const uint32_t* __restrict__ tri_color,
                       unsigned char* __restrict__ image, unsigned char* __restrict__ mask, int ntri,
                       size_t npix) {
   const int frame = blockIdx.y;
@@ -244,6 +245,8 @@ resolve_packed_kernel(const unsigned long long* __restrict__ keys, const uint32_
   const size_t base = (size_t)frame * npix + q * 4;
   const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(keys + base);
   const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(keys + base + 2);
+  *reinterpret_cast<ulonglong2*>(keys + base) = make_ulonglong2(0ull, 0ull);
+  *reinterpret_cast<ulonglong2*>(keys + base + 2) = make_ulonglong2(0ull, 0ull);
   const unsigned long long k[4] = {k01.x, k01.y, k23.x, k23.y};
   const uint32_t* tc = tri_color + (size_t)frame * ntri;
   uint32_t col[4];

@@ -1,0 +1,525 @@
+// Reconstruction kernels: the per-clip identity contraction (K0), the per-frame expression
+// basis contraction (K1, FP32 SIMT flavour; the tcgen05 flavour lives in basis_tc.cu) and the
+// fused vertex kernel (K2: normals + rotation + SH illumination + projection).
+// Reference: utils/reconstruct_mesh.py:20-29 (Shape_formation), :58-62 (Texture_formation),
+// :35-52 (Compute_norm), :100-120 (Projection_layer), :129-168 (Illumination_layer),
+// :172-223 (Reconstruction / Reconstruction_rotation).
+#include <algorithm>
+#include <vector>
+
+#include "launch.h"
+#include "ptx.cuh"
+
+namespace vp {
+
+// =========================================================================================
+// K0: out[r] = mean[r] + sum_k basis[r][k] * coeff[k]  (- center[r % 3]), float64 accumulate.
+// Runs once per clip ("identity mean precomputed once").
+// =========================================================================================
+template <typename B, typename O, int K>
+__global__ void __launch_bounds__(256)
+identity_kernel(const B* __restrict__ basis, const double* __restrict__ mean, const float* __restrict__ coeff,
+                double c0, double c1, double c2, O* __restrict__ out, int rows) {
+  __shared__ double cs[K];
+  if (threadIdx.x < K) cs[threadIdx.x] = (double)coeff[threadIdx.x];
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const B* row = basis + (size_t)r * K;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int k = 0; k < K; ++k) acc += (double)__ldg(row + k) * cs[k];
+  acc += mean[r];
+  const int axis = r % 3;
+  acc -= (axis == 0) ? c0 : (axis == 1 ? c1 : c2);
+  out[r] = static_cast<O>(acc);
+}
+
+int launch_identity(vp_model* m, const float* id_dev, const float* tex_dev, cudaStream_t st) {
+  const int grid = (m->rows + 255) / 256;
+  if (id_dev) {
+    if (m->idb64)
+      identity_kernel<double, double, VP_N_ID><<<grid, 256, 0, st>>>(
+          static_cast<const double*>(m->idb), m->meanshape, id_dev, m->center[0], m->center[1], m->center[2], m->base,
+          m->rows);
+    else
+      identity_kernel<float, double, VP_N_ID><<<grid, 256, 0, st>>>(
+          static_cast<const float*>(m->idb), m->meanshape, id_dev, m->center[0], m->center[1], m->center[2], m->base,
+          m->rows);
+    VP_LAUNCH_CHECK();
+  }
+  if (tex_dev) {
+    if (m->texb64)
+      identity_kernel<double, float, VP_N_TEX><<<grid, 256, 0, st>>>(static_cast<const double*>(m->texb), m->meantex,
+                                                                     tex_dev, 0.0, 0.0, 0.0, m->tex, m->rows);
+    else
+      identity_kernel<float, float, VP_N_TEX><<<grid, 256, 0, st>>>(static_cast<const float*>(m->texb), m->meantex,
+                                                                    tex_dev, 0.0, 0.0, 0.0, m->tex, m->rows);
+    VP_LAUNCH_CHECK();
+  }
+  return VP_OK;
+}
+
+// =========================================================================================
+// K1 (SIMT): disp[t][r] = sum_k exb[r][k] * ex[t][k], FP32.
+// One CTA owns 128 basis rows: every thread TMA-bulk-copies its own 256-byte row into a padded
+// shared-memory tile (row pitch 272 B, so the 128-bit reads below are bank-conflict free),
+// keeps the 64 coefficients of its row in registers and streams over the frames; the frame
+// coefficients are broadcast reads from shared memory.  The basis is read from HBM exactly once.
+// =========================================================================================
+constexpr int kBasisRows = 128;
+constexpr int kBasisFrames = 32;  // frames staged per pass
+constexpr int kBasisPitch = 68;   // floats
+
+__global__ void __launch_bounds__(kBasisRows)
+basis_simt_kernel(const float* __restrict__ exb, const float* __restrict__ ex, float* __restrict__ disp, int nframes,
+                  int rows_pad) {
+  __shared__ __align__(16) float a_s[kBasisRows * kBasisPitch];
+  __shared__ __align__(16) float ex_s[kBasisFrames * VP_N_EX];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int row = blockIdx.x * kBasisRows + tid;
+  if (tid == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) ptx::mbar_arrive_expect_tx(&bar, kBasisRows * VP_N_EX * sizeof(float));
+  ptx::bulk_g2s(a_s + tid * kBasisPitch, exb + (size_t)row * VP_N_EX, VP_N_EX * sizeof(float), &bar);
+  ptx::mbar_wait(&bar, 0);
+
+  float a[VP_N_EX];
+  {
+    const float4* p = reinterpret_cast<const float4*>(a_s + tid * kBasisPitch);
+#pragma unroll
+    for (int j = 0; j < VP_N_EX / 4; ++j) {
+      const float4 v = p[j];
+      a[4 * j + 0] = v.x;
+      a[4 * j + 1] = v.y;
+      a[4 * j + 2] = v.z;
+      a[4 * j + 3] = v.w;
+    }
+  }
+
+  for (int t0 = 0; t0 < nframes; t0 += kBasisFrames) {
+    const int nt = min(kBasisFrames, nframes - t0);
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(ex + (size_t)t0 * VP_N_EX);
+      float4* dst = reinterpret_cast<float4*>(ex_s);
+      for (int i = tid; i < kBasisFrames * VP_N_EX / 4; i += kBasisRows)
+        dst[i] = (i < nt * (VP_N_EX / 4)) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int t = 0; t < nt; t += 4) {  // 4 frames in flight per thread (ex_s is zero padded)
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < VP_N_EX / 4; ++j) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 e = *reinterpret_cast<const float4*>(ex_s + (t + u) * VP_N_EX + 4 * j);
+          acc[u] = fmaf(a[4 * j + 0], e.x, acc[u]);
+          acc[u] = fmaf(a[4 * j + 1], e.y, acc[u]);
+          acc[u] = fmaf(a[4 * j + 2], e.z, acc[u]);
+          acc[u] = fmaf(a[4 * j + 3], e.w, acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (t + u < nt) disp[(size_t)(t0 + t + u) * rows_pad + row] = acc[u];
+    }
+  }
+}
+
+int launch_basis_simt(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st) {
+  if (nframes == 0) return VP_OK;
+  basis_simt_kernel<<<m->rows_pad / kBasisRows, kBasisRows, 0, st>>>(m->exb, ex_dev, disp_dev, nframes, m->rows_pad);
+  VP_LAUNCH_CHECK();
+  return VP_OK;
+}
+
+int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st) {
+  return launch_basis_simt(m, ex_dev, disp_dev, nframes, st);
+}
+
+// =========================================================================================
+// K2: one CTA per (vertex tile, group of frames).  Per frame:
+//   1. local vertex positions (own + halo) = per-clip base shape (float64) + expression
+//      displacement (float32) -> shared memory, float64;
+//   2. normals of the tile's triangles: edges differenced in float64 (the cancellation-prone
+//      step), cross product in float32 -> shared memory;
+//   3. per own vertex: ring sum in point_buf slot order, normalise, rotate, 9-band SH lighting,
+//      colour, (double) rotation, perspective projection -> one float4 raster record
+//      (x, S - y, -z, rgb bytes) and/or the reference's per-vertex outputs.
+// =========================================================================================
+struct VertexArgs {
+  const TileDesc* tiles;
+  const uint32_t* ltri;
+  const int* halo;
+  const uint16_t* ring;
+  const int* v_int2orig;
+  const double* base;
+  const float* tex;
+  const float* disp;
+  size_t disp_stride;
+  const FrameParams* params;
+  int nframes;
+  int frames_per_block;
+  int rotate_first;
+  double focal, center, image_size, raster_scale;
+  float4* vrec;
+  size_t vrec_stride;
+  ReconOut out;
+  int nver;
+};
+
+__global__ void __launch_bounds__(kTileV) vertex_tile_kernel(const VertexArgs a) {
+  __shared__ double s_pos[3][kTileLV];
+  __shared__ float s_fn[3][kTileLT];
+  __shared__ FrameParams s_par;
+  static_assert(sizeof(FrameParams) == 192, "FrameParams layout");
+
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int tid = threadIdx.x;
+
+  // per-tile constants held in registers across the frame loop
+  int gv[3];
+  double bx[3], by[3], bz[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int i = tid + q * kTileV;
+    gv[q] = -1;
+    bx[q] = by[q] = bz[q] = 0.0;
+    if (i < td.nlv) {
+      gv[q] = (i < td.nv) ? td.v_begin + i : __ldg(a.halo + td.halo_off + i - td.nv);
+      bx[q] = __ldg(a.base + 3 * (size_t)gv[q]);
+      by[q] = __ldg(a.base + 3 * (size_t)gv[q] + 1);
+      bz[q] = __ldg(a.base + 3 * (size_t)gv[q] + 2);
+    }
+  }
+  uint32_t lt[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = tid + q * kTileV;
+    lt[q] = (j < td.nlt) ? __ldg(a.ltri + td.ltri_off + j) : 0u;
+  }
+  const bool own = tid < td.nv;
+  uint4 rg = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  float tr = 0.f, tg = 0.f, tb = 0.f;
+  int orig = 0;
+  if (own) {
+    rg = __ldg(reinterpret_cast<const uint4*>(a.ring) + gv[0]);
+    if (a.tex) {
+      tr = __ldg(a.tex + 3 * (size_t)gv[0]);
+      tg = __ldg(a.tex + 3 * (size_t)gv[0] + 1);
+      tb = __ldg(a.tex + 3 * (size_t)gv[0] + 2);
+    }
+    orig = __ldg(a.v_int2orig + gv[0]);
+  }
+
+  const int f_begin = blockIdx.y * a.frames_per_block;
+  const int f_end = min(a.nframes, f_begin + a.frames_per_block);
+  for (int f = f_begin; f < f_end; ++f) {
+    __syncthreads();  // the previous frame's readers are done with shared memory
+    if (tid < (int)(sizeof(FrameParams) / 4))
+      reinterpret_cast<uint32_t*>(&s_par)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.params + f) + tid);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int i = tid + q * kTileV;
+      if (i < td.nlv) {
+        double dx = 0.0, dy = 0.0, dz = 0.0;
+        if (a.disp) {
+          const float* d = a.disp + (size_t)f * a.disp_stride + 3 * (size_t)gv[q];
+          dx = (double)__ldg(d);
+          dy = (double)__ldg(d + 1);
+          dz = (double)__ldg(d + 2);
+        }
+        s_pos[0][i] = bx[q] + dx;
+        s_pos[1][i] = by[q] + dy;
+        s_pos[2][i] = bz[q] + dz;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = tid + q * kTileV;
+      if (j < td.nlt) {
+        const int i1 = lt[q] & 1023u, i2 = (lt[q] >> 10) & 1023u, i3 = (lt[q] >> 20) & 1023u;
+        // e1 = v1 - v2, e2 = v2 - v3 (reconstruct_mesh.py:44-45), differenced in float64
+        const double x2 = s_pos[0][i2], y2 = s_pos[1][i2], z2 = s_pos[2][i2];
+        const float e1x = (float)(s_pos[0][i1] - x2), e1y = (float)(s_pos[1][i1] - y2), e1z = (float)(s_pos[2][i1] - z2);
+        const float e2x = (float)(x2 - s_pos[0][i3]), e2y = (float)(y2 - s_pos[1][i3]), e2z = (float)(z2 - s_pos[2][i3]);
+        s_fn[0][j] = e1y * e2z - e1z * e2y;
+        s_fn[1][j] = e1z * e2x - e1x * e2z;
+        s_fn[2][j] = e1x * e2y - e1y * e2x;
+      }
+    }
+    __syncthreads();
+    if (!own) continue;
+
+    // vertex normal: sum of the ring in point_buf slot order (reconstruct_mesh.py:49), normalised (:50)
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    {
+      const uint32_t w[4] = {rg.x, rg.y, rg.z, rg.w};
+#pragma unroll
+      for (int s = 0; s < VP_RING; ++s) {
+        const uint32_t j = (w[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu;
+        if (j != kRingPad) {
+          nx += s_fn[0][j];
+          ny += s_fn[1][j];
+          nz += s_fn[2][j];
+        }
+      }
+    }
+    {
+      const float len = sqrtf(nx * nx + ny * ny + nz * nz);
+      nx = nx / len;  // 0/0 -> NaN for a vertex without faces, exactly like the reference
+      ny = ny / len;
+      nz = nz / len;
+    }
+    const double* R = s_par.rot;
+    // rotated normal (reconstruct_mesh.py:184 / :208) and lighting in float32
+    const float r0 = (float)R[0], r1 = (float)R[1], r2 = (float)R[2], r3 = (float)R[3], r4 = (float)R[4],
+                r5 = (float)R[5], r6 = (float)R[6], r7 = (float)R[7], r8 = (float)R[8];
+    const float nrx = nx * r0 + ny * r3 + nz * r6;
+    const float nry = nx * r1 + ny * r4 + nz * r7;
+    const float nrz = nx * r2 + ny * r5 + nz * r8;
+    float lit[3];
+    sh_lighting<float>(s_par.gamma, nrx, nry, nrz, lit);
+    const float cr = lit[0] * tr, cg = lit[1] * tg, cb = lit[2] * tb;
+
+    // geometry in float64
+    double sx = s_pos[0][tid], sy = s_pos[1][tid], sz = s_pos[2][tid];
+    if (a.rotate_first) {  // Reconstruction_rotation rotates the shape before projecting it (:211)
+      double ox, oy, oz;
+      rotate_row(R, sx, sy, sz, ox, oy, oz);
+      sx = ox;
+      sy = oy;
+      sz = oz;
+    }
+    double px, py, zb;
+    project(R, s_par.trans, a.focal, a.center, sx, sy, sz, px, py, zb);
+    const double pyf = a.image_size - py;  // reconstruct_mesh.py:187 / :215
+
+    if (a.vrec) {
+      // infer_bfmvid.py:93-105: (x, S - y, z_buffer) -> float32; colours clipped and truncated
+      const uint32_t rgba = clip_trunc_byte(cr) | (clip_trunc_byte(cg) << 8) | (clip_trunc_byte(cb) << 16);
+      a.vrec[(size_t)f * a.vrec_stride + gv[0]] =
+          make_float4((float)(px * a.raster_scale), (float)(pyf * a.raster_scale), (float)zb, __uint_as_float(rgba));
+    }
+    const size_t o = (size_t)f * a.nver + orig;
+    if (a.out.shape) {
+      a.out.shape[3 * o] = sx;
+      a.out.shape[3 * o + 1] = sy;
+      a.out.shape[3 * o + 2] = sz;
+    }
+    if (a.out.norm) {
+      a.out.norm[3 * o] = nx;
+      a.out.norm[3 * o + 1] = ny;
+      a.out.norm[3 * o + 2] = nz;
+    }
+    if (a.out.color) {
+      a.out.color[3 * o] = cr;
+      a.out.color[3 * o + 1] = cg;
+      a.out.color[3 * o + 2] = cb;
+    }
+    if (a.out.proj) {
+      a.out.proj[2 * o] = px;
+      a.out.proj[2 * o + 1] = a.out.flip_y ? pyf : py;
+    }
+    if (a.out.zbuf) a.out.zbuf[o] = zb;
+  }
+}
+
+int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes, int rotate_first,
+                  double focal, double center, double image_size, double raster_scale, float4* vrec_dev,
+                  const ReconOut& out, cudaStream_t st) {
+  if (nframes == 0 || m->ntiles == 0) return VP_OK;
+  VertexArgs a;
+  a.tiles = m->tiles;
+  a.ltri = m->ltri;
+  a.halo = m->halo;
+  a.ring = m->ring;
+  a.v_int2orig = m->v_int2orig_dev;
+  a.base = m->base;
+  a.tex = m->have_tex ? m->tex : nullptr;
+  a.disp = disp_dev;
+  a.disp_stride = (size_t)m->rows_pad;
+  a.params = params_dev;
+  a.nframes = nframes;
+  a.frames_per_block = nframes >= 16 ? 4 : 1;
+  a.rotate_first = rotate_first;
+  a.focal = focal;
+  a.center = center;
+  a.image_size = image_size;
+  a.raster_scale = raster_scale;
+  a.vrec = vrec_dev;
+  a.vrec_stride = (size_t)m->vrec_stride;
+  a.out = out;
+  a.nver = m->nver;
+  dim3 grid(m->ntiles, (nframes + a.frames_per_block - 1) / a.frames_per_block);
+  vertex_tile_kernel<<<grid, kTileV, 0, st>>>(a);
+  VP_LAUNCH_CHECK();
+  return VP_OK;
+}
+
+// =========================================================================================
+// Illumination_layer on caller-supplied arrays (reconstruct_mesh.py:129-168), float64.
+// =========================================================================================
+__global__ void illumination_kernel(const double* __restrict__ texture, const double* __restrict__ norm,
+                                    const float* __restrict__ gamma, double* __restrict__ color,
+                                    double* __restrict__ lighting, int n) {
+  __shared__ float g[VP_N_GAMMA];
+  if (threadIdx.x < VP_N_GAMMA) g[threadIdx.x] = gamma[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double lit[3];
+  sh_lighting<double>(g, norm[3 * (size_t)i], norm[3 * (size_t)i + 1], norm[3 * (size_t)i + 2], lit);
+  for (int c = 0; c < 3; ++c) {
+    if (color) color[3 * (size_t)i + c] = lit[c] * texture[3 * (size_t)i + c];
+    if (lighting) lighting[3 * (size_t)i + c] = lit[c] * 128.0;
+  }
+}
+
+// Projection_layer on a caller-supplied shape (reconstruct_mesh.py:100-120), float64.
+__global__ void projection_kernel(const double* __restrict__ shape, FrameParams par, double focal, double center,
+                                  double* __restrict__ proj, double* __restrict__ zbuf, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double px, py, zb;
+  project(par.rot, par.trans, focal, center, shape[3 * (size_t)i], shape[3 * (size_t)i + 1], shape[3 * (size_t)i + 2],
+          px, py, zb);
+  proj[2 * (size_t)i] = px;
+  proj[2 * (size_t)i + 1] = py;
+  zbuf[i] = zb;
+}
+
+}  // namespace vp
+
+using namespace vp;
+
+static int illumination_impl(DevBuf& buf, int device, int n, const double* texture, const double* norm,
+                             const float* gamma, double* color, double* lighting) {
+  const size_t vb = (size_t)n * 3 * sizeof(double);
+  VP_CUDA(buf.reserve(4 * vb + 256, device));
+  char* b = buf.as<char>();
+  double *d_tex = reinterpret_cast<double*>(b), *d_norm = reinterpret_cast<double*>(b + vb),
+         *d_col = reinterpret_cast<double*>(b + 2 * vb), *d_lit = reinterpret_cast<double*>(b + 3 * vb);
+  float* d_gamma = reinterpret_cast<float*>(b + 4 * vb);
+  if (texture) VP_CUDA(cudaMemcpy(d_tex, texture, vb, cudaMemcpyHostToDevice));
+  VP_CUDA(cudaMemcpy(d_norm, norm, vb, cudaMemcpyHostToDevice));
+  VP_CUDA(cudaMemcpy(d_gamma, gamma, VP_N_GAMMA * sizeof(float), cudaMemcpyHostToDevice));
+  illumination_kernel<<<(n + 255) / 256, 256>>>(d_tex, d_norm, d_gamma, color ? d_col : nullptr,
+                                                lighting ? d_lit : nullptr, n);
+  VP_LAUNCH_CHECK();
+  if (color) VP_CUDA(cudaMemcpy(color, d_col, vb, cudaMemcpyDeviceToHost));
+  if (lighting) VP_CUDA(cudaMemcpy(lighting, d_lit, vb, cudaMemcpyDeviceToHost));
+  return VP_OK;
+}
+
+extern "C" int vp_illumination(int device, int n, const double* texture, const double* norm, const float* gamma,
+                               double* color, double* lighting) {
+  VP_REQUIRE(n >= 0 && norm && gamma && (color == nullptr || texture != nullptr), "null argument");
+  if (n == 0) return VP_OK;
+  VP_CUDA(cudaSetDevice(device));
+  DevBuf buf;
+  const int rc = illumination_impl(buf, device, n, texture, norm, gamma, color, lighting);
+  buf.release();
+  return rc;
+}
+
+static int projection_impl(DevBuf& buf, int device, int n, const double* shape, const double* rotation,
+                           const float* translation, double focal, double center, double* projection,
+                           double* z_buffer) {
+  const size_t vb = (size_t)n * sizeof(double);
+  VP_CUDA(buf.reserve(6 * vb, device));
+  double* d_shape = buf.as<double>();
+  double* d_proj = d_shape + 3 * (size_t)n;
+  double* d_z = d_proj + 2 * (size_t)n;
+  FrameParams par;
+  for (int k = 0; k < 9; ++k) par.rot[k] = rotation[k];
+  for (int k = 0; k < 3; ++k) par.trans[k] = translation[k];
+  for (int k = 0; k < VP_N_GAMMA; ++k) par.gamma[k] = 0.f;
+  VP_CUDA(cudaMemcpy(d_shape, shape, 3 * vb, cudaMemcpyHostToDevice));
+  projection_kernel<<<(n + 255) / 256, 256>>>(d_shape, par, focal, center, d_proj, d_z, n);
+  VP_LAUNCH_CHECK();
+  VP_CUDA(cudaMemcpy(projection, d_proj, 2 * vb, cudaMemcpyDeviceToHost));
+  VP_CUDA(cudaMemcpy(z_buffer, d_z, vb, cudaMemcpyDeviceToHost));
+  return VP_OK;
+}
+
+extern "C" int vp_projection(int device, int n, const double* shape, const double* rotation9,
+                             const float* translation3, double focal, double center, double* projection,
+                             double* z_buffer) {
+  VP_REQUIRE(n >= 0 && shape && rotation9 && translation3 && projection && z_buffer, "null argument");
+  if (n == 0) return VP_OK;
+  VP_CUDA(cudaSetDevice(device));
+  DevBuf buf;
+  const int rc = projection_impl(buf, device, n, shape, rotation9, translation3, focal, center, projection, z_buffer);
+  buf.release();
+  return rc;
+}
+
+// Reconstruction / Reconstruction_rotation for `frames->nframes` coefficient rows at once.
+extern "C" int vp_reconstruct(vp_model* m, const vp_frames* fr, const vp_recon_out* out) {
+  VP_REQUIRE(m != nullptr && fr != nullptr && out != nullptr, "null argument");
+  VP_REQUIRE(fr->nframes >= 0, "nframes >= 0");
+  VP_REQUIRE(fr->nframes == 0 || (fr->rotation && fr->translation && fr->gamma), "null per-frame array");
+  std::lock_guard<std::mutex> lock(m->mu);
+  VP_REQUIRE(m->have_base, "no base shape (call vp_set_identity or vp_set_base_shape first)");
+  VP_REQUIRE(!out->face_color || m->have_tex, "face_color requested but no texture set");
+  VP_CUDA(cudaSetDevice(m->device));
+  cudaStream_t st = nullptr;
+  const int T = fr->nframes;
+  const int chunk = 64;
+  const size_t nv = (size_t)m->nver;
+  for (int t0 = 0; t0 < T; t0 += chunk) {
+    const int n = std::min(chunk, T - t0);
+    // per-frame parameters
+    std::vector<FrameParams> hp((size_t)n);
+    for (int i = 0; i < n; ++i) {
+      const size_t t = (size_t)t0 + i;
+      for (int k = 0; k < 9; ++k) hp[i].rot[k] = fr->rotation[9 * t + k];
+      for (int k = 0; k < 3; ++k) hp[i].trans[k] = fr->translation[3 * t + k];
+      for (int k = 0; k < VP_N_GAMMA; ++k) hp[i].gamma[k] = fr->gamma[VP_N_GAMMA * t + k];
+    }
+    VP_CUDA(m->ws_params.reserve((size_t)chunk * sizeof(FrameParams), m->device));
+    VP_CUDA(cudaMemcpyAsync(m->ws_params.ptr, hp.data(), (size_t)n * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+    float* disp = nullptr;
+    if (fr->ex) {
+      VP_CUDA(m->ws_ex.reserve((size_t)chunk * VP_N_EX * sizeof(float), m->device));
+      VP_CUDA(m->ws_disp.reserve((size_t)chunk * m->rows_pad * sizeof(float), m->device));
+      VP_CUDA(cudaMemcpyAsync(m->ws_ex.ptr, fr->ex + (size_t)t0 * VP_N_EX, (size_t)n * VP_N_EX * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+      disp = m->ws_disp.as<float>();
+      VP_TRY(launch_basis(m, m->ws_ex.as<float>(), disp, n, st));
+    }
+    // outputs: carve one scratch allocation
+    const size_t b_shape = out->face_shape ? nv * 3 * sizeof(double) * n : 0;
+    const size_t b_norm = out->face_norm ? nv * 3 * sizeof(float) * n : 0;
+    const size_t b_color = out->face_color ? nv * 3 * sizeof(float) * n : 0;
+    const size_t b_proj = out->projection ? nv * 2 * sizeof(double) * n : 0;
+    const size_t b_z = out->z_buffer ? nv * sizeof(double) * n : 0;
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    VP_CUDA(m->ws_out.reserve(al(b_shape) + al(b_norm) + al(b_color) + al(b_proj) + al(b_z) + 256, m->device));
+    char* p = m->ws_out.as<char>();
+    ReconOut ro;
+    ro.flip_y = out->flip_y;
+    if (b_shape) { ro.shape = reinterpret_cast<double*>(p); p += al(b_shape); }
+    if (b_proj) { ro.proj = reinterpret_cast<double*>(p); p += al(b_proj); }
+    if (b_z) { ro.zbuf = reinterpret_cast<double*>(p); p += al(b_z); }
+    if (b_norm) { ro.norm = reinterpret_cast<float*>(p); p += al(b_norm); }
+    if (b_color) { ro.color = reinterpret_cast<float*>(p); p += al(b_color); }
+    VP_TRY(launch_vertex(m, disp, m->ws_params.as<FrameParams>(), n, fr->rotate_shape_first, fr->focal, fr->center,
+                         out->image_size, 1.0, nullptr, ro, st));
+    const size_t off = (size_t)t0 * nv;
+    if (b_shape) VP_CUDA(cudaMemcpyAsync(out->face_shape + 3 * off, ro.shape, b_shape, cudaMemcpyDeviceToHost, st));
+    if (b_norm) VP_CUDA(cudaMemcpyAsync(out->face_norm + 3 * off, ro.norm, b_norm, cudaMemcpyDeviceToHost, st));
+    if (b_color) VP_CUDA(cudaMemcpyAsync(out->face_color + 3 * off, ro.color, b_color, cudaMemcpyDeviceToHost, st));
+    if (b_proj) VP_CUDA(cudaMemcpyAsync(out->projection + 2 * off, ro.proj, b_proj, cudaMemcpyDeviceToHost, st));
+    if (b_z) VP_CUDA(cudaMemcpyAsync(out->z_buffer + off, ro.zbuf, b_z, cudaMemcpyDeviceToHost, st));
+    VP_CUDA(cudaStreamSynchronize(st));
+  }
+  return VP_OK;
+}

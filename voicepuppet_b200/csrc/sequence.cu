@@ -1,0 +1,241 @@
+// The whole hot path, coefficients -> rendered frames: the batched replacement of the frame
+// loop in voicepuppet/pixrefer/infer_bfmvid.py:231-243 (render_face, :79-109, per frame).
+// Frames are processed in chunks sized so that every intermediate (displacements, vertex
+// records, z-buffer keys, per-triangle colours) stays resident in the 126 MB L2; per chunk the
+// launches are K1 basis -> K2 vertex -> K3 scatter -> K4 resolve.
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "launch.h"
+
+namespace vp {
+
+namespace {
+
+size_t env_size(const char* name, size_t dflt) {
+  const char* s = std::getenv(name);
+  if (!s || !*s) return dflt;
+  const long long v = std::atoll(s);
+  return v > 0 ? (size_t)v : dflt;
+}
+
+int chunk_frames(const vp_model* m, int res, int nframes) {
+  const size_t per_frame = (size_t)m->rows_pad * 4 + (size_t)m->vrec_stride * 16 + (size_t)res * res * 8 +
+                           (size_t)m->ntri * 4;
+  const size_t forced = env_size("VPB200_CHUNK_FRAMES", 0);
+  size_t c = forced ? forced : (env_size("VPB200_CHUNK_MB", 64) << 20) / per_frame;
+  c = std::max<size_t>(c, 4);
+  c = std::min<size_t>(c, 1024);
+  c = std::min<size_t>(c, (size_t)std::max(nframes, 1));
+  return (int)c;
+}
+
+struct Profiler {
+  vp_model* m;
+  cudaStream_t st;
+  std::vector<cudaEvent_t> ev;
+  explicit Profiler(vp_model* m_, cudaStream_t st_) : m(m_), st(st_) {}
+  void mark() {
+    if (!m->profiling) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    ev.push_back(e);
+  }
+  // events come in groups of kProfSlots + 1 per chunk
+  void finish() {
+    if (!m->profiling) return;
+    cudaStreamSynchronize(st);
+    for (int k = 0; k < kProfSlots; ++k) m->prof_ms[k] = 0.f;
+    for (size_t g = 0; g + kProfSlots < ev.size(); g += kProfSlots + 1)
+      for (int k = 0; k < kProfSlots; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[g + k], ev[g + k + 1]) == cudaSuccess) m->prof_ms[k] += ms;
+      }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+
+int reserve_chunk(vp_model* m, int chunk, int res) {
+  const size_t npix = (size_t)res * res;
+  VP_CUDA(m->ws_disp.reserve((size_t)chunk * m->rows_pad * sizeof(float), m->device));
+  VP_CUDA(m->ws_vrec.reserve((size_t)chunk * m->vrec_stride * sizeof(float4), m->device));
+  VP_CUDA(m->ws_tricol.reserve((size_t)chunk * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
+  const size_t key_bytes = (size_t)chunk * npix * sizeof(unsigned long long);
+  void* before = m->ws_keys.ptr;
+  VP_CUDA(m->ws_keys.reserve(key_bytes, m->device));
+  if (m->ws_keys.ptr != before) m->keys_clean_bytes = 0;
+  return VP_OK;
+}
+
+// one chunk, everything on the device, nothing synchronised
+int render_chunk(vp_model* m, int n, const float* ex_dev, const FrameParams* params_dev, int rotate_first, int res,
+                 unsigned char* image_dev, unsigned char* mask_dev, cudaStream_t st, Profiler& prof) {
+  const size_t npix = (size_t)res * res;
+  const size_t key_bytes = (size_t)n * npix * sizeof(unsigned long long);
+  if (m->keys_clean_bytes < key_bytes) {  // the resolve pass leaves the keys it consumed zeroed
+    VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
+    m->keys_clean_bytes = m->ws_keys.cap;
+  }
+  float* disp = m->ws_disp.as<float>();
+  float4* vrec = m->ws_vrec.as<float4>();
+  unsigned long long* keys = m->ws_keys.as<unsigned long long>();
+  uint32_t* tricol = m->ws_tricol.as<uint32_t>();
+  prof.mark();
+  if (ex_dev) VP_TRY(launch_basis(m, ex_dev, disp, n, st));
+  prof.mark();
+  ReconOut none;
+  VP_TRY(launch_vertex(m, ex_dev ? disp : nullptr, params_dev, n, rotate_first, 1015.0, 112.0, 224.0,
+                       (double)res / 224.0, vrec, none, st));
+  prof.mark();
+  VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, n, m->ntri, res, res, st));
+  prof.mark();
+  VP_TRY(launch_resolve_packed(keys, tricol, image_dev, mask_dev, n, m->ntri, res, res, st));
+  prof.mark();
+  return VP_OK;
+}
+
+int check_sequence_args(const vp_model* m, int nframes, int res, const void* image) {
+  VP_REQUIRE(m != nullptr, "null model");
+  VP_REQUIRE(nframes >= 0, "nframes >= 0");
+  VP_REQUIRE(res >= 2 && res <= 8192 && res % 2 == 0, "res must be even and in 2..8192");
+  VP_REQUIRE(nframes == 0 || image != nullptr, "null image buffer");
+  return VP_OK;
+}
+
+}  // namespace
+}  // namespace vp
+
+using namespace vp;
+
+extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev, const vp_frame_params* params_dev,
+                                      int rotate_shape_first, int res, unsigned char* image_dev,
+                                      unsigned char* face_mask_dev, void* stream) {
+  VP_TRY(check_sequence_args(m, nframes, res, image_dev));
+  VP_REQUIRE(nframes == 0 || params_dev != nullptr, "null params");
+  if (nframes == 0) return VP_OK;
+  std::lock_guard<std::mutex> lock(m->mu);
+  VP_REQUIRE(m->have_base && m->have_tex, "no identity set (call vp_set_identity first)");
+  VP_CUDA(cudaSetDevice(m->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunk = chunk_frames(m, res, nframes);
+  VP_TRY(reserve_chunk(m, chunk, res));
+  const size_t npix = (size_t)res * res;
+  Profiler prof(m, st);
+  int rc = VP_OK;
+  for (int t0 = 0; t0 < nframes && rc == VP_OK; t0 += chunk) {
+    const int n = std::min(chunk, nframes - t0);
+    rc = render_chunk(m, n, ex_dev ? ex_dev + (size_t)t0 * VP_N_EX : nullptr,
+                      reinterpret_cast<const FrameParams*>(params_dev) + t0, rotate_shape_first, res,
+                      image_dev + (size_t)t0 * npix * 3, face_mask_dev ? face_mask_dev + (size_t)t0 * npix : nullptr,
+                      st, prof);
+  }
+  if (rc != VP_OK) m->keys_clean_bytes = 0;
+  prof.finish();
+  return rc;
+}
+
+extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, unsigned char* image,
+                                  unsigned char* face_mask, int outputs_on_device, void* stream) {
+  VP_REQUIRE(fr != nullptr, "null frames");
+  VP_TRY(check_sequence_args(m, fr->nframes, res, image));
+  const int T = fr->nframes;
+  if (T == 0) return VP_OK;
+  VP_REQUIRE(fr->rotation && fr->translation && fr->gamma, "null per-frame array");
+  VP_REQUIRE(fr->focal == 1015.0 && fr->center == 112.0, "the fused path renders with focal 1015 / center 112");
+  std::lock_guard<std::mutex> lock(m->mu);
+  VP_REQUIRE(m->have_base && m->have_tex, "no identity set (call vp_set_identity first)");
+  VP_CUDA(cudaSetDevice(m->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // per-frame inputs: one upload for the whole sequence (T * 448 bytes)
+  std::vector<FrameParams> hp((size_t)T);
+  for (int t = 0; t < T; ++t) {
+    for (int k = 0; k < 9; ++k) hp[t].rot[k] = fr->rotation[9 * (size_t)t + k];
+    for (int k = 0; k < 3; ++k) hp[t].trans[k] = fr->translation[3 * (size_t)t + k];
+    for (int k = 0; k < VP_N_GAMMA; ++k) hp[t].gamma[k] = fr->gamma[VP_N_GAMMA * (size_t)t + k];
+  }
+  VP_CUDA(m->ws_params.reserve((size_t)T * sizeof(FrameParams), m->device));
+  VP_CUDA(cudaMemcpyAsync(m->ws_params.ptr, hp.data(), (size_t)T * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+  if (fr->ex) {
+    VP_CUDA(m->ws_ex.reserve((size_t)T * VP_N_EX * sizeof(float), m->device));
+    VP_CUDA(cudaMemcpyAsync(m->ws_ex.ptr, fr->ex, (size_t)T * VP_N_EX * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  const float* ex_dev = fr->ex ? m->ws_ex.as<float>() : nullptr;
+  const FrameParams* params_dev = m->ws_params.as<FrameParams>();
+
+  const int chunk = chunk_frames(m, res, T);
+  VP_TRY(reserve_chunk(m, chunk, res));
+  const size_t npix = (size_t)res * res;
+  Profiler prof(m, st);
+  int rc = VP_OK;
+  if (outputs_on_device) {
+    for (int t0 = 0; t0 < T && rc == VP_OK; t0 += chunk) {
+      const int n = std::min(chunk, T - t0);
+      rc = render_chunk(m, n, ex_dev ? ex_dev + (size_t)t0 * VP_N_EX : nullptr, params_dev + t0,
+                        fr->rotate_shape_first, res, image + (size_t)t0 * npix * 3,
+                        face_mask ? face_mask + (size_t)t0 * npix : nullptr, st, prof);
+    }
+    if (rc == VP_OK) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+        rc = VP_ERR_CUDA;
+      }
+    }
+  } else {
+    // double-buffered: chunk i renders while chunk i-1 drains to the host on the copy stream
+    for (int b = 0; b < 2; ++b) {
+      VP_CUDA(m->ws_img[b].reserve((size_t)chunk * npix * 3, m->device));
+      if (face_mask) VP_CUDA(m->ws_mask[b].reserve((size_t)chunk * npix, m->device));
+    }
+    int ci = 0;
+    for (int t0 = 0; t0 < T && rc == VP_OK; t0 += chunk, ++ci) {
+      const int n = std::min(chunk, T - t0);
+      const int b = ci & 1;
+      if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(st, m->ev_copy[b], 0));
+      rc = render_chunk(m, n, ex_dev ? ex_dev + (size_t)t0 * VP_N_EX : nullptr, params_dev + t0,
+                        fr->rotate_shape_first, res, m->ws_img[b].as<unsigned char>(),
+                        face_mask ? m->ws_mask[b].as<unsigned char>() : nullptr, st, prof);
+      if (rc != VP_OK) break;
+      VP_CUDA(cudaEventRecord(m->ev_render[b], st));
+      VP_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_render[b], 0));
+      VP_CUDA(cudaMemcpyAsync(image + (size_t)t0 * npix * 3, m->ws_img[b].ptr, (size_t)n * npix * 3,
+                              cudaMemcpyDeviceToHost, m->copy_stream));
+      if (face_mask)
+        VP_CUDA(cudaMemcpyAsync(face_mask + (size_t)t0 * npix, m->ws_mask[b].ptr, (size_t)n * npix,
+                                cudaMemcpyDeviceToHost, m->copy_stream));
+      VP_CUDA(cudaEventRecord(m->ev_copy[b], m->copy_stream));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(st);
+    cudaError_t e2 = cudaStreamSynchronize(m->copy_stream);
+    if (rc == VP_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+      set_error("stream synchronize failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      rc = VP_ERR_CUDA;
+    }
+  }
+  if (rc != VP_OK) m->keys_clean_bytes = 0;
+  prof.finish();
+  return rc;
+}
+
+extern "C" int vp_set_profiling(vp_model* m, int enabled) {
+  VP_REQUIRE(m != nullptr, "null model");
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->profiling = enabled != 0;
+  return VP_OK;
+}
+
+extern "C" int vp_get_profile(vp_model* m, char* names, int names_cap, float* ms, int ms_cap) {
+  VP_REQUIRE(m != nullptr, "null model");
+  std::lock_guard<std::mutex> lock(m->mu);
+  static const char kNames[] = "basis;vertex;scatter;resolve";
+  if (names && names_cap > 0) {
+    std::snprintf(names, (size_t)names_cap, "%s", kNames);
+  }
+  for (int k = 0; k < kProfSlots && k < ms_cap; ++k)
+    if (ms) ms[k] = m->prof_ms[k];
+  return VP_OK;
+}

@@ -1,0 +1,213 @@
+// One-off mesh analysis behind vp_model_create (host only, no CUDA calls).
+//
+// The reference recomputes vertex normals per frame with two fancy-index gathers over the
+// whole mesh (utils/reconstruct_mesh.py:35-52: shape[tri] and face_norm[point_buf]).  Here the
+// adjacency is compiled once into vertex TILES: up to 128 spatially adjacent vertices, the
+// triangles their point_buf rows name and the halo vertices those triangles touch, all with
+// tile-local indices, so that the per-frame vertex kernel works out of shared memory.
+//   * vertices are renumbered along a Morton curve of the mean shape's (x, y);
+//   * a tile is a run of consecutive renumbered vertices, grown greedily until it would
+//     exceed 128 own vertices, kTileLV local vertices or kTileLT local triangles;
+//   * point_buf slot order is preserved (the reference sums the ring in column order);
+//   * triangles are renumbered by their smallest renumbered vertex for the rasterizer, and
+//     keep their ORIGINAL index for the z-buffer tie-break.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "launch.h"
+
+namespace vp {
+
+namespace {
+
+uint32_t spread16(uint32_t v) {
+  v &= 0xFFFFu;
+  v = (v | (v << 8)) & 0x00FF00FFu;
+  v = (v | (v << 4)) & 0x0F0F0F0Fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+
+uint32_t quantize(double v, double lo, double hi) {
+  if (!(hi > lo) || !(v == v)) return 0;
+  double q = (v - lo) / (hi - lo) * 65535.0;
+  if (q < 0) q = 0;
+  if (q > 65535.0) q = 65535.0;
+  return (uint32_t)q;
+}
+
+}  // namespace
+
+int build_topology(Topology& out, int nver, int ntri, const int* tri, const int* point_buf, const double* xyz) {
+  VP_REQUIRE(nver >= 0 && ntri >= 0, "negative element count");
+  VP_REQUIRE(nver == 0 || (point_buf && xyz), "null model array");
+  VP_REQUIRE(ntri == 0 || tri, "null triangle array");
+  for (size_t i = 0; i < (size_t)ntri * 3; ++i)
+    VP_REQUIRE(tri[i] >= 0 && tri[i] < nver, "triangle index out of range");
+
+  out = Topology();
+  out.nver = nver;
+  out.ntri = ntri;
+
+  // ---- Morton order of the vertices ------------------------------------------------------
+  double lo[2] = {INFINITY, INFINITY}, hi[2] = {-INFINITY, -INFINITY};
+  for (int v = 0; v < nver; ++v)
+    for (int a = 0; a < 2; ++a) {
+      const double c = xyz[3 * (size_t)v + a];
+      if (c == c && std::fabs(c) != INFINITY) {
+        lo[a] = std::min(lo[a], c);
+        hi[a] = std::max(hi[a], c);
+      }
+    }
+  std::vector<uint32_t> code(nver);
+  for (int v = 0; v < nver; ++v)
+    code[v] = spread16(quantize(xyz[3 * (size_t)v], lo[0], hi[0])) |
+              (spread16(quantize(xyz[3 * (size_t)v + 1], lo[1], hi[1])) << 1);
+  out.v_int2orig.resize(nver);
+  std::iota(out.v_int2orig.begin(), out.v_int2orig.end(), 0);
+  std::stable_sort(out.v_int2orig.begin(), out.v_int2orig.end(),
+                   [&](int a, int b) { return code[a] < code[b]; });
+  out.v_orig2int.resize(nver);
+  for (int i = 0; i < nver; ++i) out.v_orig2int[out.v_int2orig[i]] = i;
+
+  // ---- triangles for the rasterizer ------------------------------------------------------
+  std::vector<int> t_order(ntri);
+  std::iota(t_order.begin(), t_order.end(), 0);
+  std::vector<int> t_key(ntri);
+  for (int f = 0; f < ntri; ++f)
+    t_key[f] = std::min(out.v_orig2int[tri[3 * (size_t)f]],
+                        std::min(out.v_orig2int[tri[3 * (size_t)f + 1]], out.v_orig2int[tri[3 * (size_t)f + 2]]));
+  std::stable_sort(t_order.begin(), t_order.end(), [&](int a, int b) { return t_key[a] < t_key[b]; });
+  out.tri_int.resize((size_t)ntri * 4);
+  for (int i = 0; i < ntri; ++i) {
+    const int f = t_order[i];
+    out.tri_int[4 * (size_t)i + 0] = out.v_orig2int[tri[3 * (size_t)f]];
+    out.tri_int[4 * (size_t)i + 1] = out.v_orig2int[tri[3 * (size_t)f + 1]];
+    out.tri_int[4 * (size_t)i + 2] = out.v_orig2int[tri[3 * (size_t)f + 2]];
+    out.tri_int[4 * (size_t)i + 3] = f;
+  }
+
+  // ---- vertex tiles ----------------------------------------------------------------------
+  out.ring.assign((size_t)nver * VP_RING, kRingPad);
+  std::vector<int> tri_stamp(ntri, -1), tri_local(ntri, 0);   // tile id that last saw the triangle
+  std::vector<int> ver_stamp(nver, -1), ver_local(nver, 0);   // ... the (internal) vertex
+  std::vector<int> cur_tris, cur_touched;                     // in first-seen order
+  int v = 0;
+  while (v < nver) {
+    const int tile_id = (int)out.tiles.size();
+    TileDesc td;
+    td.v_begin = v;
+    td.nv = 0;
+    cur_tris.clear();
+    cur_touched.clear();
+    int n_touched = 0;  // distinct internal vertices that are own or touched
+    while (v < nver && td.nv < kTileV) {
+      // what would adding internal vertex v cost?
+      const int ov = out.v_int2orig[v];
+      int new_t[VP_RING], n_new_t = 0;
+      int new_v[3 * VP_RING + 1], n_new_v = 0;
+      auto want_vertex = [&](int iv) {
+        if (ver_stamp[iv] == tile_id) return;
+        for (int k = 0; k < n_new_v; ++k)
+          if (new_v[k] == iv) return;
+        new_v[n_new_v++] = iv;
+      };
+      want_vertex(v);
+      for (int s = 0; s < VP_RING; ++s) {
+        const int f = point_buf[(size_t)ov * VP_RING + s];
+        if (f < 0 || f >= ntri || tri_stamp[f] == tile_id) continue;
+        bool dup = false;
+        for (int k = 0; k < n_new_t; ++k) dup |= (new_t[k] == f);
+        if (dup) continue;
+        new_t[n_new_t++] = f;
+        for (int c = 0; c < 3; ++c) want_vertex(out.v_orig2int[tri[3 * (size_t)f + c]]);
+      }
+      if (td.nv > 0 && ((int)cur_tris.size() + n_new_t > kTileLT || n_touched + n_new_v > kTileLV)) break;
+      for (int k = 0; k < n_new_t; ++k) {
+        tri_stamp[new_t[k]] = tile_id;
+        tri_local[new_t[k]] = (int)cur_tris.size();
+        cur_tris.push_back(new_t[k]);
+      }
+      for (int k = 0; k < n_new_v; ++k) {
+        ver_stamp[new_v[k]] = tile_id;
+        cur_touched.push_back(new_v[k]);
+      }
+      n_touched += n_new_v;
+      for (int s = 0; s < VP_RING; ++s) {
+        const int f = point_buf[(size_t)ov * VP_RING + s];
+        if (f >= 0 && f < ntri) out.ring[(size_t)v * VP_RING + s] = (uint16_t)tri_local[f];
+      }
+      ++td.nv;
+      ++v;
+    }
+    // local numbering: own vertices 0..nv-1 in internal order, then the halo in first-seen order
+    td.halo_off = (int)out.halo.size();
+    int next = td.nv;
+    for (int iv : cur_touched) {
+      if (iv >= td.v_begin && iv < td.v_begin + td.nv) {
+        ver_local[iv] = iv - td.v_begin;
+      } else {
+        ver_local[iv] = next++;
+        out.halo.push_back(iv);
+      }
+    }
+    td.nlv = next;
+    td.nlt = (int)cur_tris.size();
+    td.ltri_off = (int)out.ltri.size();
+    for (int f : cur_tris) {
+      const uint32_t a = (uint32_t)ver_local[out.v_orig2int[tri[3 * (size_t)f]]];
+      const uint32_t b = (uint32_t)ver_local[out.v_orig2int[tri[3 * (size_t)f + 1]]];
+      const uint32_t c = (uint32_t)ver_local[out.v_orig2int[tri[3 * (size_t)f + 2]]];
+      out.ltri.push_back(a | (b << 10) | (c << 20));
+    }
+    out.tiles.push_back(td);
+  }
+  return VP_OK;
+}
+
+}  // namespace vp
+
+// ---- introspection entry points (host only; used by the CPU test-suite) --------------------
+struct vp_topology {
+  vp::Topology t;
+};
+
+extern "C" int vp_topology_build(vp_topology** out, int nver, int ntri, const int* tri, const int* point_buf,
+                                 const double* xyz) {
+  VP_REQUIRE(out != nullptr, "null out pointer");
+  *out = nullptr;
+  vp_topology* h = new vp_topology();
+  const int rc = vp::build_topology(h->t, nver, ntri, tri, point_buf, xyz);
+  if (rc != VP_OK) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return VP_OK;
+}
+
+extern "C" void vp_topology_destroy(vp_topology* h) { delete h; }
+
+extern "C" int vp_topology_sizes(const vp_topology* h, int* ntiles, int* nltri, int* nhalo) {
+  VP_REQUIRE(h != nullptr, "null handle");
+  if (ntiles) *ntiles = (int)h->t.tiles.size();
+  if (nltri) *nltri = (int)h->t.ltri.size();
+  if (nhalo) *nhalo = (int)h->t.halo.size();
+  return VP_OK;
+}
+
+extern "C" int vp_topology_copy(const vp_topology* h, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
+                                int* halo, uint16_t* ring) {
+  VP_REQUIRE(h != nullptr, "null handle");
+  const vp::Topology& t = h->t;
+  if (v_int2orig) std::memcpy(v_int2orig, t.v_int2orig.data(), t.v_int2orig.size() * sizeof(int));
+  if (tri_int) std::memcpy(tri_int, t.tri_int.data(), t.tri_int.size() * sizeof(int));
+  if (tiles) std::memcpy(tiles, t.tiles.data(), t.tiles.size() * sizeof(vp::TileDesc));
+  if (ltri) std::memcpy(ltri, t.ltri.data(), t.ltri.size() * sizeof(uint32_t));
+  if (halo) std::memcpy(halo, t.halo.data(), t.halo.size() * sizeof(int));
+  if (ring) std::memcpy(ring, t.ring.data(), t.ring.size() * sizeof(uint16_t));
+  return VP_OK;
+}

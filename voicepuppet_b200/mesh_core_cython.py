@@ -1,0 +1,96 @@
+"""Drop-in for the reference's native rasterizer module ``utils/cython/mesh_core_cython.pyx``.
+
+    from voicepuppet_b200 import mesh_core_cython
+    mesh_core_cython.render_colors_core(image, face_mask, vertices, triangles, colors, depth_buffer,
+                                        ntri, h, w, c)
+
+Same contract as the Cython wrappers (mesh_core_cython.pyx:49-78): the caller allocates and
+pre-initialises every buffer, the call mutates them in place and returns None; ``None`` arguments
+raise TypeError, wrong dtype / ndim / non-contiguous arrays raise ValueError like Cython's typed
+buffer check.  The work is done by libvpb200.so's z-buffer kernels (order-independent 64-bit
+(depth, triangle) atomicMax + resolve), bit-identical to the reference's sequential C++ loop
+(utils/cython/mesh_core.cpp:108-231).
+"""
+import numpy as np
+
+from . import _lib
+
+__all__ = ['render_colors_core', 'rasterize_triangles_core']
+
+
+def _buffer(name, a, dtype, ndim):
+  if a is None:
+    raise TypeError("Argument '%s' must not be None" % name)
+  if not isinstance(a, np.ndarray):
+    raise TypeError("Argument '%s' has incorrect type (expected numpy.ndarray, got %s)" % (name, type(a).__name__))
+  if a.dtype != dtype:
+    raise ValueError("Buffer dtype mismatch, expected '%s' but got '%s'" % (np.dtype(dtype).name, a.dtype.name))
+  if a.ndim != ndim:
+    raise ValueError('Buffer has wrong number of dimensions (expected %d, got %d)' % (ndim, a.ndim))
+  if not a.flags.c_contiguous:
+    raise ValueError('ndarray is not C-contiguous')
+  return a
+
+
+def _need(name, a, count):
+  if a.size < count:
+    raise ValueError("buffer '%s' holds %d elements, the call needs %d" % (name, a.size, count))
+
+
+def render_colors_core(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c):
+  """mesh_core_cython.pyx:64-78 -> mesh_core.cpp:169-231 (flat depth, flat colour)."""
+  image = _buffer('image', image, np.uint8, 1)
+  face_mask = _buffer('face_mask', face_mask, np.uint8, 1)
+  vertices = _buffer('vertices', vertices, np.float32, 1)
+  triangles = _buffer('triangles', triangles, np.int32, 1)
+  colors = _buffer('colors', colors, np.float32, 1)
+  depth_buffer = _buffer('depth_buffer', depth_buffer, np.float32, 1)
+  ntri, h, w, c = int(ntri), int(h), int(w), int(c)
+  nver = vertices.size // 3
+  _need('image', image, h * w * c)
+  _need('face_mask', face_mask, h * w)
+  _need('depth_buffer', depth_buffer, h * w)
+  _need('triangles', triangles, 3 * ntri)
+  _need('colors', colors, c * nver)
+  if ntri > 0:
+    t = triangles[:3 * ntri]
+    if t.min() < 0 or t.max() >= nver:
+      raise ValueError('triangle index outside the vertex buffer (the reference would read out of bounds)')
+  _lib.check(_lib.lib().vp_render_colors_core(_lib.ptr(image), _lib.ptr(face_mask), _lib.ptr(vertices),
+                                              _lib.ptr(triangles), _lib.ptr(colors), _lib.ptr(depth_buffer), None,
+                                              nver, ntri, h, w, c))
+
+
+def render_colors_with_triangle_id(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c):
+  """render_colors_core that also returns the winning triangle per pixel (-1 = untouched), which
+  the reference computes implicitly but never stores."""
+  triangle_id = np.empty(int(h) * int(w), dtype=np.int32)
+  nver = vertices.size // 3
+  _lib.check(_lib.lib().vp_render_colors_core(_lib.ptr(image), _lib.ptr(face_mask), _lib.ptr(vertices),
+                                              _lib.ptr(triangles), _lib.ptr(colors), _lib.ptr(depth_buffer),
+                                              _lib.ptr(triangle_id), nver, int(ntri), int(h), int(w), int(c)))
+  return triangle_id
+
+
+def rasterize_triangles_core(vertices, triangles, depth_buffer, triangle_buffer, barycentric_weight, nver, ntri, h,
+                             w):
+  """mesh_core_cython.pyx:49-62 -> mesh_core.cpp:108-166 (interpolated depth, triangle id and
+  barycentric weights, the 2-pixel border rule)."""
+  vertices = _buffer('vertices', vertices, np.float32, 2)
+  triangles = _buffer('triangles', triangles, np.int32, 2)
+  depth_buffer = _buffer('depth_buffer', depth_buffer, np.float32, 2)
+  triangle_buffer = _buffer('triangle_buffer', triangle_buffer, np.int32, 2)
+  barycentric_weight = _buffer('barycentric_weight', barycentric_weight, np.float32, 2)
+  nver, ntri, h, w = int(nver), int(ntri), int(h), int(w)
+  _need('vertices', vertices, 3 * nver)
+  _need('triangles', triangles, 3 * ntri)
+  _need('depth_buffer', depth_buffer, h * w)
+  _need('triangle_buffer', triangle_buffer, h * w)
+  _need('barycentric_weight', barycentric_weight, 3 * h * w)
+  if ntri > 0:
+    t = triangles.reshape(-1)[:3 * ntri]
+    if t.min() < 0 or t.max() >= nver:
+      raise ValueError('triangle index outside the vertex buffer (the reference would read out of bounds)')
+  _lib.check(_lib.lib().vp_rasterize_triangles_core(_lib.ptr(vertices), _lib.ptr(triangles), _lib.ptr(depth_buffer),
+                                                    _lib.ptr(triangle_buffer), _lib.ptr(barycentric_weight), nver,
+                                                    ntri, h, w))

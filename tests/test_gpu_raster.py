@@ -145,10 +145,15 @@ def test_empty_and_degenerate_inputs():
   cols = np.zeros((3, 3), dtype=np.float32)
   image, mask, depth = gpu_colors(verts, np.zeros((0, 3), np.int32), cols, 8, 8)
   assert not image.any() and not mask.any() and np.all(depth == np.float32(-99999.0))
-  # zero-area triangle on a pixel centre: never inside (inverDeno = 0)
+  # zero-area triangle on a pixel centre: inverDeno = 0 makes u = v = 0, which the reference's test
+  # (u >= 0 && v >= 0 && u + v < 1, mesh_core.cpp:49) accepts -- one pixel is drawn
   verts = np.array([[2, 2, 1], [2, 2, 1], [2, 2, 1]], dtype=np.float32)
-  image, mask, depth = gpu_colors(verts, np.array([[0, 1, 2]], np.int32), cols, 8, 8)
-  assert not mask.any()
+  tri = np.array([[0, 1, 2]], np.int32)
+  a = gpu_colors(verts, tri, cols, 8, 8, want_tid=True)
+  b = cpu_colors(verts, tri, cols, 8, 8)
+  for x, y in zip(a, b):
+    assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+  assert a[1].sum() == 255 and a[1].reshape(8, 8)[2, 2] == 255
 
 
 def test_idempotent_second_pass(golden_full, full_model):

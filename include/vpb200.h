@@ -123,6 +123,10 @@ int vp_topology_sizes(const vp_topology* t, int* ntiles, int* nltri, int* nhalo)
 int vp_topology_copy(const vp_topology* t, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
                      int* halo, uint16_t* ring);
 
+/* Expression-basis kernel selection: 0 = automatic (FP32 streamed kernel below 16 frames per launch,
+ * tcgen05 3xTF32 GEMM from 16 frames up), 1 = always FP32 SIMT, 2 = always tcgen05 3xTF32. */
+int vp_set_basis_mode(vp_model* m, int mode);
+
 /* Per-clip constants ("identity mean precomputed once"): base shape = meanshape + idBase.id
  * - center, texture = meantex + texBase.tex.  Either pointer may be NULL to keep the old one. */
 int vp_set_identity(vp_model* m, const float* id_coeff80, const float* tex_coeff80);

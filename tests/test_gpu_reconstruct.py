@@ -111,3 +111,31 @@ def test_linearity_of_the_expression_basis(full_model):
   s2 = rm.Shape_formation(idc, c[2:3, 80:144], full_model) - s0
   s12 = rm.Shape_formation(idc, c[1:2, 80:144] + c[2:3, 80:144], full_model) - s0
   assert np.max(np.abs(s12 - (s1 + s2))) < 2e-7
+
+
+@pytest.mark.parametrize('t', [16, 75, 130])
+def test_tensor_core_basis_matches_fp32_and_fp64(full_model, t):
+  """K1: the tcgen05 3xTF32 GEMM against the FP32 SIMT kernel and a float64 numpy contraction
+  (Shape_formation's expression einsum, reconstruct_mesh.py:21-22)."""
+  from voicepuppet_b200 import _lib
+  from voicepuppet_b200.model import DeviceModel
+  dm = DeviceModel.of(full_model)
+  coeffs = synthetic.make_coeffs(t, seed=3)
+  dm.set_identity(coeffs[0:1, :80], coeffs[0:1, 144:224])
+  base = dm.get_base_shape()
+  eye = np.tile(np.eye(3).reshape(1, 9), (t, 1))
+  z3, z27 = np.zeros((t, 3), np.float32), np.zeros((t, 27), np.float32)
+  out = {}
+  try:
+    for mode in (1, 2):
+      _lib.check(_lib.lib().vp_set_basis_mode(dm.handle, mode))
+      out[mode] = dm.reconstruct(coeffs[:, 80:144], eye, z3, z27, want=('shape',))['shape']
+  finally:
+    _lib.check(_lib.lib().vp_set_basis_mode(dm.handle, 0))
+  want = base[None] + np.einsum('ij,tj->ti', full_model.exBase.astype(np.float32).astype(np.float64),
+                                coeffs[:, 80:144].astype(np.float64)).reshape(t, -1, 3)
+  disp_scale = float(np.abs(want - base[None]).max())
+  for mode in (1, 2):
+    err = float(np.abs(out[mode] - want).max())
+    assert err < 4e-7 * max(1.0, disp_scale), (mode, err)      # fp32-grade accuracy of the displacement
+  assert float(np.abs(out[1] - out[2]).max()) < 4e-7

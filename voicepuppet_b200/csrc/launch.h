@@ -90,6 +90,9 @@ struct vp_model {
   uint32_t* ltri = nullptr;
   int* halo = nullptr;
   uint16_t* ring = nullptr;     // [nver][8] local triangle index per point_buf slot
+  // TMA descriptor of exb for the tcgen05 basis kernel (a CUtensorMap, kept opaque here)
+  alignas(64) unsigned char tmap_exb[128] = {0};
+  bool have_tmap = false;
   // device: per-clip state
   double* base = nullptr;       // [nver][3]
   float* tex = nullptr;         // [nver][3]
@@ -102,6 +105,7 @@ struct vp_model {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 
+  int basis_mode = 0;           // vp::BasisMode
   // profiling
   bool profiling = false;
   float prof_ms[8] = {0};
@@ -116,6 +120,12 @@ enum ProfSlot { kProfBasis = 0, kProfVertex = 1, kProfScatter = 2, kProfResolve 
 // ---- reconstruction (reconstruct.cu) ----------------------------------------------------
 int launch_identity(vp_model* m, const float* id_dev, const float* tex_dev, cudaStream_t st);
 int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st);
+int launch_basis_simt(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st);
+// tcgen05 3xTF32 flavour (basis_tc.cu); basis_tc_prepare builds the TMA descriptor once per model
+int basis_tc_prepare(vp_model* m);
+int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st);
+enum BasisMode { kBasisAuto = 0, kBasisSimt = 1, kBasisTensor = 2 };
+constexpr int kBasisTensorMinFrames = 16;  // below this the frame batch is a GEMV, not a dense contraction
 // disp_dev may be NULL (no expression displacement).  vrec_dev may be NULL (no raster records).
 int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes,
                   int rotate_first, double focal, double center, double image_size, double raster_scale,

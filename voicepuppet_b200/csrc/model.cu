@@ -154,6 +154,8 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
   VP_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->coeff_tmp), 160 * sizeof(float)));
   VP_CUDA(cudaMemset(m->coeff_tmp, 0, 160 * sizeof(float)));
 
+  if (basis_tc_prepare(m) != VP_OK) m->have_tmap = false;  // the SIMT kernel still works; mode 2 reports it
+
   VP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     VP_CUDA(cudaEventCreateWithFlags(&m->ev_render[i], cudaEventDisableTiming));
@@ -190,6 +192,15 @@ extern "C" void vp_model_destroy(vp_model* m) { free_model(m); }
 extern "C" int vp_model_nver(const vp_model* m) { return m ? m->nver : -1; }
 extern "C" int vp_model_ntri(const vp_model* m) { return m ? m->ntri : -1; }
 extern "C" int vp_model_ntiles(const vp_model* m) { return m ? m->ntiles : -1; }
+
+extern "C" int vp_set_basis_mode(vp_model* m, int mode) {
+  VP_REQUIRE(m != nullptr, "null model");
+  VP_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (FP32 SIMT) or 2 (tcgen05 3xTF32)");
+  std::lock_guard<std::mutex> lock(m->mu);
+  VP_REQUIRE(mode != kBasisTensor || m->have_tmap, "tensor-core basis kernel unavailable on this device/driver");
+  m->basis_mode = mode;
+  return VP_OK;
+}
 
 extern "C" int vp_set_identity(vp_model* m, const float* id_coeff80, const float* tex_coeff80) {
   VP_REQUIRE(m != nullptr, "null model");

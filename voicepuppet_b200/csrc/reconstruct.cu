@@ -138,8 +138,16 @@ int launch_basis_simt(vp_model* m, const float* ex_dev, float* disp_dev, int nfr
   return VP_OK;
 }
 
+// FP32 streamed kernel for GEMV-like batches, tcgen05 3xTF32 GEMM once the frame batch is a real
+// dense contraction (BASELINE.json north_star); vp_set_basis_mode overrides the choice.
 int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st) {
-  return launch_basis_simt(m, ex_dev, disp_dev, nframes, st);
+  bool tensor = m->have_tmap && nframes >= kBasisTensorMinFrames;
+  if (m->basis_mode == kBasisSimt) tensor = false;
+  if (m->basis_mode == kBasisTensor) {
+    VP_REQUIRE(m->have_tmap, "tensor-core basis kernel unavailable (no TMA descriptor)");
+    tensor = true;
+  }
+  return tensor ? launch_basis_tc(m, ex_dev, disp_dev, nframes, st) : launch_basis_simt(m, ex_dev, disp_dev, nframes, st);
 }
 
 // =========================================================================================

@@ -20,6 +20,9 @@ size_t env_size(const char* name, size_t dflt) {
   return v > 0 ? (size_t)v : dflt;
 }
 
+// Frames per raster chunk: the chunk's vertex records, z-buffer keys and per-triangle colours
+// (plus its slice of the displacements) should stay L2 resident (VPB200_CHUNK_MB, default 64 MB);
+// the sequence is then cut into equal chunks so that no launch runs nearly empty.
 int chunk_frames(const vp_model* m, int res, int nframes) {
   const size_t per_frame = (size_t)m->rows_pad * 4 + (size_t)m->vrec_stride * 16 + (size_t)res * res * 8 +
                            (size_t)m->ntri * 4;
@@ -27,40 +30,57 @@ int chunk_frames(const vp_model* m, int res, int nframes) {
   size_t c = forced ? forced : (env_size("VPB200_CHUNK_MB", 64) << 20) / per_frame;
   c = std::max<size_t>(c, 4);
   c = std::min<size_t>(c, 1024);
-  c = std::min<size_t>(c, (size_t)std::max(nframes, 1));
-  return (int)c;
+  const size_t t = (size_t)std::max(nframes, 1);
+  if (forced) return (int)std::min(c, t);
+  const size_t nchunks = std::max<size_t>(1, (t * 10 + c * 11 - 1) / (c * 11));  // ceil(t / (1.1 c))
+  return (int)((t + nchunks - 1) / nchunks);
 }
 
+// CUDA-event pairs around individual launches, summed per slot when profiling is enabled.
 struct Profiler {
   vp_model* m;
   cudaStream_t st;
-  std::vector<cudaEvent_t> ev;
+  struct Span { int slot; cudaEvent_t a, b; };
+  std::vector<Span> spans;
   explicit Profiler(vp_model* m_, cudaStream_t st_) : m(m_), st(st_) {}
-  void mark() {
+  void begin(int slot) {
     if (!m->profiling) return;
-    cudaEvent_t e;
-    if (cudaEventCreate(&e) != cudaSuccess) return;
-    cudaEventRecord(e, st);
-    ev.push_back(e);
+    Span s{slot, nullptr, nullptr};
+    if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+    cudaEventRecord(s.a, st);
+    spans.push_back(s);
   }
-  // events come in groups of kProfSlots + 1 per chunk
+  void end() {
+    if (!m->profiling || spans.empty()) return;
+    cudaEventRecord(spans.back().b, st);
+  }
   void finish() {
     if (!m->profiling) return;
     cudaStreamSynchronize(st);
     for (int k = 0; k < kProfSlots; ++k) m->prof_ms[k] = 0.f;
-    for (size_t g = 0; g + kProfSlots < ev.size(); g += kProfSlots + 1)
-      for (int k = 0; k < kProfSlots; ++k) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ev[g + k], ev[g + k + 1]) == cudaSuccess) m->prof_ms[k] += ms;
-      }
-    for (cudaEvent_t e : ev) cudaEventDestroy(e);
-    ev.clear();
+    for (const Span& s : spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) m->prof_ms[s.slot] += ms;
+      cudaEventDestroy(s.a);
+      cudaEventDestroy(s.b);
+    }
+    spans.clear();
   }
 };
 
-int reserve_chunk(vp_model* m, int chunk, int res) {
+// The basis contraction runs over a larger group of frames than the raster chunk (one pass over
+// the 27 MB basis per group); its output for 96 frames (41 MB) still sits in L2 next to the basis.
+int basis_group_frames(int chunk, int nframes) {
+  const int cap = (int)env_size("VPB200_BASIS_FRAMES", 96);
+  const int t = std::max(nframes, 1);
+  const int ngroups = (t + cap - 1) / cap;
+  const int per_group = (t + ngroups - 1) / ngroups;
+  return (per_group + chunk - 1) / chunk * chunk;  // a whole number of raster chunks
+}
+
+int reserve_chunk(vp_model* m, int chunk, int group, int res) {
   const size_t npix = (size_t)res * res;
-  VP_CUDA(m->ws_disp.reserve((size_t)chunk * m->rows_pad * sizeof(float), m->device));
+  VP_CUDA(m->ws_disp.reserve((size_t)group * m->rows_pad * sizeof(float), m->device));  // >= any group
   VP_CUDA(m->ws_vrec.reserve((size_t)chunk * m->vrec_stride * sizeof(float4), m->device));
   VP_CUDA(m->ws_tricol.reserve((size_t)chunk * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
   const size_t key_bytes = (size_t)chunk * npix * sizeof(unsigned long long);
@@ -70,8 +90,8 @@ int reserve_chunk(vp_model* m, int chunk, int res) {
   return VP_OK;
 }
 
-// one chunk, everything on the device, nothing synchronised
-int render_chunk(vp_model* m, int n, const float* ex_dev, const FrameParams* params_dev, int rotate_first, int res,
+// one chunk, everything on the device, nothing synchronised; disp_dev holds this chunk's displacements
+int render_chunk(vp_model* m, int n, const float* disp_dev, const FrameParams* params_dev, int rotate_first, int res,
                  unsigned char* image_dev, unsigned char* mask_dev, cudaStream_t st, Profiler& prof) {
   const size_t npix = (size_t)res * res;
   const size_t key_bytes = (size_t)n * npix * sizeof(unsigned long long);
@@ -79,21 +99,30 @@ int render_chunk(vp_model* m, int n, const float* ex_dev, const FrameParams* par
     VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
     m->keys_clean_bytes = m->ws_keys.cap;
   }
-  float* disp = m->ws_disp.as<float>();
   float4* vrec = m->ws_vrec.as<float4>();
   unsigned long long* keys = m->ws_keys.as<unsigned long long>();
   uint32_t* tricol = m->ws_tricol.as<uint32_t>();
-  prof.mark();
-  if (ex_dev) VP_TRY(launch_basis(m, ex_dev, disp, n, st));
-  prof.mark();
   ReconOut none;
-  VP_TRY(launch_vertex(m, ex_dev ? disp : nullptr, params_dev, n, rotate_first, 1015.0, 112.0, 224.0,
-                       (double)res / 224.0, vrec, none, st));
-  prof.mark();
+  prof.begin(kProfVertex);
+  VP_TRY(launch_vertex(m, disp_dev, params_dev, n, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, vrec, none,
+                       st));
+  prof.end();
+  prof.begin(kProfScatter);
   VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, n, m->ntri, res, res, st));
-  prof.mark();
+  prof.end();
+  prof.begin(kProfResolve);
   VP_TRY(launch_resolve_packed(keys, tricol, image_dev, mask_dev, n, m->ntri, res, res, st));
-  prof.mark();
+  prof.end();
+  return VP_OK;
+}
+
+// frames [t0, t0 + n) start a new basis group: contract the whole group's expression coefficients
+int basis_group(vp_model* m, const float* ex_dev, int t0, int total, int group, cudaStream_t st, Profiler& prof) {
+  if (!ex_dev) return VP_OK;
+  const int n = std::min(group, total - t0);
+  prof.begin(kProfBasis);
+  VP_TRY(launch_basis(m, ex_dev + (size_t)t0 * VP_N_EX, m->ws_disp.as<float>(), n, st));
+  prof.end();
   return VP_OK;
 }
 
@@ -121,13 +150,16 @@ extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_
   VP_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunk = chunk_frames(m, res, nframes);
-  VP_TRY(reserve_chunk(m, chunk, res));
+  const int group = basis_group_frames(chunk, nframes);
+  VP_TRY(reserve_chunk(m, chunk, group, res));
   const size_t npix = (size_t)res * res;
   Profiler prof(m, st);
   int rc = VP_OK;
   for (int t0 = 0; t0 < nframes && rc == VP_OK; t0 += chunk) {
     const int n = std::min(chunk, nframes - t0);
-    rc = render_chunk(m, n, ex_dev ? ex_dev + (size_t)t0 * VP_N_EX : nullptr,
+    if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, nframes, group, st, prof);
+    if (rc != VP_OK) break;
+    rc = render_chunk(m, n, ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr,
                       reinterpret_cast<const FrameParams*>(params_dev) + t0, rotate_shape_first, res,
                       image_dev + (size_t)t0 * npix * 3, face_mask_dev ? face_mask_dev + (size_t)t0 * npix : nullptr,
                       st, prof);
@@ -167,15 +199,18 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
   const FrameParams* params_dev = m->ws_params.as<FrameParams>();
 
   const int chunk = chunk_frames(m, res, T);
-  VP_TRY(reserve_chunk(m, chunk, res));
+  const int group = basis_group_frames(chunk, T);
+  VP_TRY(reserve_chunk(m, chunk, group, res));
   const size_t npix = (size_t)res * res;
   Profiler prof(m, st);
   int rc = VP_OK;
   if (outputs_on_device) {
     for (int t0 = 0; t0 < T && rc == VP_OK; t0 += chunk) {
       const int n = std::min(chunk, T - t0);
-      rc = render_chunk(m, n, ex_dev ? ex_dev + (size_t)t0 * VP_N_EX : nullptr, params_dev + t0,
-                        fr->rotate_shape_first, res, image + (size_t)t0 * npix * 3,
+      if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, T, group, st, prof);
+      if (rc != VP_OK) break;
+      rc = render_chunk(m, n, ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr,
+                        params_dev + t0, fr->rotate_shape_first, res, image + (size_t)t0 * npix * 3,
                         face_mask ? face_mask + (size_t)t0 * npix : nullptr, st, prof);
     }
     if (rc == VP_OK) {
@@ -196,8 +231,10 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
       const int n = std::min(chunk, T - t0);
       const int b = ci & 1;
       if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(st, m->ev_copy[b], 0));
-      rc = render_chunk(m, n, ex_dev ? ex_dev + (size_t)t0 * VP_N_EX : nullptr, params_dev + t0,
-                        fr->rotate_shape_first, res, m->ws_img[b].as<unsigned char>(),
+      if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, T, group, st, prof);
+      if (rc != VP_OK) break;
+      rc = render_chunk(m, n, ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr,
+                        params_dev + t0, fr->rotate_shape_first, res, m->ws_img[b].as<unsigned char>(),
                         face_mask ? m->ws_mask[b].as<unsigned char>() : nullptr, st, prof);
       if (rc != VP_OK) break;
       VP_CUDA(cudaEventRecord(m->ev_render[b], st));

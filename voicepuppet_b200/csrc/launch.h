@@ -16,11 +16,15 @@ namespace vp {
 int launch_keys_from_depth(const float* depth_dev, unsigned long long* keys_dev, size_t n, cudaStream_t st);
 int launch_scatter_generic(int mode, const float* vertices, size_t frame_stride, const int* triangles,
                            unsigned long long* keys, int nframes, int ntri, int h, int w, cudaStream_t st);
+// Fused path: keys carry the chunk's epoch in their top bits (see EpochKey in raster.cuh), so the
+// z-buffer is cleared only when the epoch counter wraps (epoch_limit) or the buffer is reallocated.
+uint32_t epoch_limit(int ntri);
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
-                          unsigned long long* keys, uint32_t* tri_color, int nframes, int ntri, int h, int w,
+                          unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
+                          int w, cudaStream_t st);
+int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, uint32_t epoch,
+                          unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
                           cudaStream_t st);
-int launch_resolve_packed(unsigned long long* keys, const uint32_t* tri_color, unsigned char* image,
-                          unsigned char* mask, int nframes, int ntri, int h, int w, cudaStream_t st);
 
 // ---- vertex-tile topology (topology.cpp builds it, reconstruct.cu consumes it) ----------
 constexpr int kTileV = 128;    // max own vertices per tile == threads per CTA of the vertex kernel
@@ -101,7 +105,7 @@ struct vp_model {
 
   // workspaces (grow only)
   vp::DevBuf ws_ex, ws_params, ws_disp, ws_vrec, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
-  size_t keys_clean_bytes = 0;  // prefix of ws_keys known to be all-zero
+  uint32_t key_epoch = 0;       // epoch of the last chunk rendered into ws_keys (0 = buffer must be cleared)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 

@@ -36,30 +36,50 @@ int launch_scatter_generic(int mode, const float* vertices, size_t frame_stride,
   GenericMesh mesh{vertices, triangles, frame_stride};
   dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, nframes);
   if (mode == kModeColors)
-    raster_scatter_kernel<kModeColors, GenericMesh><<<grid, kRasterBlock, 0, st>>>(mesh, keys, nullptr, ntri, h, w, 0);
+    raster_scatter_kernel<kModeColors, GenericMesh, FullKey><<<grid, kRasterBlock, 0, st>>>(mesh, FullKey(), keys, nullptr,
+                                                                                         ntri, h, w, 0);
   else
-    raster_scatter_kernel<kModeTriangles, GenericMesh><<<grid, kRasterBlock, 0, st>>>(mesh, keys, nullptr, ntri, h, w, 0);
+    raster_scatter_kernel<kModeTriangles, GenericMesh, FullKey><<<grid, kRasterBlock, 0, st>>>(mesh, FullKey(), keys,
+                                                                                            nullptr, ntri, h, w, 0);
   VP_LAUNCH_CHECK();
   return VP_OK;
+}
+
+// Epoch keys need the inverted triangle index to fit next to a 32-bit depth code and >= 1 epoch bit.
+int epoch_tri_bits(int ntri) {
+  int bits = 1;
+  while (bits < 31 && (1ll << bits) < (long long)ntri + 1) ++bits;
+  return bits;
+}
+uint32_t epoch_limit(int ntri) { return (1u << (32 - epoch_tri_bits(ntri))) - 1u; }  // largest usable epoch
+
+static EpochKey make_epoch_key(int ntri, uint32_t epoch) {
+  EpochKey km;
+  km.tri_bits = epoch_tri_bits(ntri);
+  km.tri_mask = (1u << km.tri_bits) - 1u;
+  km.epoch_field = static_cast<unsigned long long>(epoch) << (32 + km.tri_bits);
+  return km;
 }
 
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
-                          unsigned long long* keys, uint32_t* tri_color, int nframes, int ntri, int h, int w,
-                          cudaStream_t st) {
+                          unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
+                          int w, cudaStream_t st) {
   if (ntri == 0 || nframes == 0) return VP_OK;
   PackedMesh mesh{vrec, triangles, frame_stride};
   dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, nframes);
-  raster_scatter_kernel<kModeColors, PackedMesh><<<grid, kRasterBlock, 0, st>>>(mesh, keys, tri_color, ntri, h, w, 1);
+  raster_scatter_kernel<kModeColors, PackedMesh, EpochKey><<<grid, kRasterBlock, 0, st>>>(
+      mesh, make_epoch_key(ntri, epoch), keys, tri_color, ntri, h, w, 1);
   VP_LAUNCH_CHECK();
   return VP_OK;
 }
 
-int launch_resolve_packed(unsigned long long* keys, const uint32_t* tri_color, unsigned char* image,
-                          unsigned char* mask, int nframes, int ntri, int h, int w, cudaStream_t st) {
+int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, uint32_t epoch,
+                          unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
+                          cudaStream_t st) {
   const size_t npix = (size_t)h * w;
   if (nframes == 0 || npix == 0) return VP_OK;
   dim3 grid((unsigned)((npix / 4 + 255) / 256), nframes);
-  resolve_packed_kernel<<<grid, 256, 0, st>>>(keys, tri_color, image, mask, ntri, npix);
+  resolve_packed_kernel<<<grid, 256, 0, st>>>(keys, make_epoch_key(ntri, epoch), tri_color, image, mask, ntri, npix);
   VP_LAUNCH_CHECK();
   return VP_OK;
 }

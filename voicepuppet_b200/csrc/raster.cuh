@@ -15,7 +15,7 @@
 namespace vp {
 
 constexpr int kRasterBlock = 256;
-constexpr int kSmallBox = 8;  // boxes up to this many pixels are walked by the owning lane
+constexpr int kSmallBox = 12;  // boxes up to this many pixels are walked by the owning lane
 
 enum RasterMode { kModeColors = 0, kModeTriangles = 1 };
 
@@ -62,40 +62,69 @@ struct PackedMesh {
   }
 };
 
-struct Candidate {  // what one lane knows about its triangle
-  TriSetup s;
-  float z0, z1, z2;  // kModeTriangles: per-corner depth; kModeColors: z0 = flat depth
-  uint32_t id;
-  int n;             // bbox pixel count (0 = nothing to do)
+// Key flavours.  FullKey: 32-bit depth code | 32-bit inverted triangle index, compared against keys
+// initialised from the caller's depth buffer (the mesh_core_cython entry points).  EpochKey: the
+// fused pipeline's variant -- [epoch | depth code | inverted index in `tri_bits` bits]; a key
+// written by an earlier chunk carries a smaller epoch and loses every atomicMax, so the z-buffer
+// never has to be cleared between chunks (the resolve pass treats a stale epoch as background).
+struct FullKey {
+  __device__ __forceinline__ unsigned long long make(float d, uint32_t tri) const { return make_key(d, tri); }
+};
+struct EpochKey {
+  unsigned long long epoch_field;  // epoch << (32 + tri_bits)
+  uint32_t tri_mask;               // (1 << tri_bits) - 1
+  int tri_bits;
+  __device__ __forceinline__ unsigned long long make(float d, uint32_t tri) const {
+    return epoch_field | (static_cast<unsigned long long>(depth_code(d)) << tri_bits) |
+           static_cast<unsigned long long>(tri_mask - tri);
+  }
 };
 
-template <int MODE>
-__device__ __forceinline__ void offer_pixel(const Candidate& c, int j, unsigned long long* keys, int h, int w) {
-  const int bw = c.s.x_hi - c.s.x_lo + 1;
-  const int y = c.s.y_lo + j / bw;
-  const int x = c.s.x_lo + j % bw;
-  float u, v;
-  pixel_uv(c.s, x, y, u, v);
-  if (MODE == kModeColors) {
-    if (uv_inside(u, v)) atomicMax(keys + (size_t)y * w + x, make_key(c.z0, c.id));
-  } else {
-    if (in_border(x, y, h, w) || uv_inside(u, v)) {
-      float w0, w1, w2;
-      const float d = weights_depth(u, v, c.z0, c.z1, c.z2, w0, w1, w2);
-      if (d == d) atomicMax(keys + (size_t)y * w + x, make_key(d, c.id));
+struct Candidate {  // what one lane knows about its triangle
+  TriSetup s;
+  float z0, z1, z2;             // kModeTriangles: per-corner depth
+  unsigned long long key;       // kModeColors: the triangle's key (flat depth, index)
+  uint32_t id;
+  int n;                        // bbox pixel count (0 = nothing to do)
+};
+
+// One pixel row of the bounding box.  The row terms e0y*py / e1y*py are hoisted: they are the
+// same individually rounded products pixel_uv() forms (mesh_core.cpp:29,34,36).
+template <int MODE, typename KeyMaker>
+__device__ __forceinline__ void offer_span(const Candidate& c, const KeyMaker& km, int y, int x_begin, int x_end,
+                                           int x_step, unsigned long long* keys, int h, int w) {
+  const float py = VP_SUB(static_cast<float>(y), c.s.ay);
+  const float m0y = VP_MUL(c.s.e0y, py), m1y = VP_MUL(c.s.e1y, py);
+  unsigned long long* row = keys + (size_t)y * w;
+  for (int x = x_begin; x <= x_end; x += x_step) {
+    const float px = VP_SUB(static_cast<float>(x), c.s.ax);
+    const float d02 = VP_ADD(VP_MUL(c.s.e0x, px), m0y);
+    const float d12 = VP_ADD(VP_MUL(c.s.e1x, px), m1y);
+    const float u = VP_MUL(VP_SUB(VP_MUL(c.s.d11, d02), VP_MUL(c.s.d01, d12)), c.s.inv);
+    const float v = VP_MUL(VP_SUB(VP_MUL(c.s.d00, d12), VP_MUL(c.s.d01, d02)), c.s.inv);
+    if (MODE == kModeColors) {
+      if (uv_inside(u, v)) atomicMax(row + x, c.key);
+    } else {
+      if (in_border(x, y, h, w) || uv_inside(u, v)) {
+        float w0, w1, w2;
+        const float d = weights_depth(u, v, c.z0, c.z1, c.z2, w0, w1, w2);
+        if (d == d) atomicMax(row + x, km.make(d, c.id));
+      }
     }
   }
 }
 
-// One lane per triangle; boxes larger than kSmallBox are walked by the whole warp.
-// tri_color (may be NULL, kModeColors + PackedMesh only): flat colour per ORIGINAL triangle
-// index, written here so that the resolve pass needs one gather per pixel.
-// const_init: keys start at 0 and the initial depth is the constant kInitDepth, so the
-// strict "d > initial" test is done here per triangle instead of through init keys.
-template <int MODE, typename Mesh>
+// One lane per triangle.  Boxes of up to kSmallBox pixels are walked by the owning lane; larger
+// ones are broadcast through shared memory and walked by the whole warp, one row per iteration.
+// tri_color (may be NULL, kModeColors + PackedMesh only): flat colour per ORIGINAL triangle index,
+// written here so that the resolve pass needs one gather per pixel.
+// const_init: the initial depth is the constant kInitDepth (infer_bfmvid.py:106), so the strict
+// "d > initial" test (mesh_core.cpp:211) is done here per triangle instead of through init keys.
+template <int MODE, typename Mesh, typename KeyMaker>
 __global__ void __launch_bounds__(kRasterBlock)
-raster_scatter_kernel(Mesh mesh, unsigned long long* __restrict__ keys, uint32_t* __restrict__ tri_color,
-                      int ntri, int h, int w, int const_init) {
+raster_scatter_kernel(Mesh mesh, KeyMaker km, unsigned long long* __restrict__ keys,
+                      uint32_t* __restrict__ tri_color, int ntri, int h, int w, int const_init) {
+  __shared__ Candidate s_big[kRasterBlock / 32];
   const int frame = blockIdx.y;
   const int f = blockIdx.x * kRasterBlock + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
@@ -104,6 +133,7 @@ raster_scatter_kernel(Mesh mesh, unsigned long long* __restrict__ keys, uint32_t
   Candidate c;
   c.n = 0;
   c.id = 0;
+  c.key = 0ull;
   c.z0 = c.z1 = c.z2 = 0.f;
   if (f < ntri) {
     int ia, ib, ic;
@@ -114,13 +144,12 @@ raster_scatter_kernel(Mesh mesh, unsigned long long* __restrict__ keys, uint32_t
     mesh.vertex(frame, ib, x1, y1, z1, r1);
     mesh.vertex(frame, ic, x2, y2, z2, r2);
     if (tri_bbox(c.s, x0, y0, x1, y1, x2, y2, h, w)) {
-      tri_edges(c.s, x0, y0, x1, y1, x2, y2);
       c.n = (c.s.x_hi - c.s.x_lo + 1) * (c.s.y_hi - c.s.y_lo + 1);
       if (MODE == kModeColors) {
         const float d = flat_depth(z0, z1, z2);
-        c.z0 = d;
         if (!(d == d)) c.n = 0;                          // NaN never wins a '>' test
         if (const_init && !(d > kInitDepth)) c.n = 0;    // mesh_core.cpp:211 against -99999
+        c.key = km.make(d, c.id);
         if (tri_color != nullptr && c.n > 0) {
           // integral colours in [0,255] packed by the vertex kernel: sum <= 765 is exact in float,
           // so integer arithmetic equals mesh_core.cpp:219
@@ -134,41 +163,32 @@ raster_scatter_kernel(Mesh mesh, unsigned long long* __restrict__ keys, uint32_t
         c.z1 = z1;
         c.z2 = z2;
       }
+      if (c.n > 0) tri_edges(c.s, x0, y0, x1, y1, x2, y2);
     }
   }
 
   if (c.n > 0 && c.n <= kSmallBox) {
-    for (int j = 0; j < c.n; ++j) offer_pixel<MODE>(c, j, keys, h, w);
+    for (int y = c.s.y_lo; y <= c.s.y_hi; ++y) offer_span<MODE>(c, km, y, c.s.x_lo, c.s.x_hi, 1, keys, h, w);
   }
   unsigned big = __ballot_sync(0xFFFFFFFFu, c.n > kSmallBox);
+  Candidate* slot = &s_big[threadIdx.x >> 5];
   while (big) {
     const int src = __ffs(big) - 1;
     big &= big - 1;
-    Candidate o;
-    o.s.ax = __shfl_sync(0xFFFFFFFFu, c.s.ax, src);
-    o.s.ay = __shfl_sync(0xFFFFFFFFu, c.s.ay, src);
-    o.s.e0x = __shfl_sync(0xFFFFFFFFu, c.s.e0x, src);
-    o.s.e0y = __shfl_sync(0xFFFFFFFFu, c.s.e0y, src);
-    o.s.e1x = __shfl_sync(0xFFFFFFFFu, c.s.e1x, src);
-    o.s.e1y = __shfl_sync(0xFFFFFFFFu, c.s.e1y, src);
-    o.s.d00 = __shfl_sync(0xFFFFFFFFu, c.s.d00, src);
-    o.s.d01 = __shfl_sync(0xFFFFFFFFu, c.s.d01, src);
-    o.s.d11 = __shfl_sync(0xFFFFFFFFu, c.s.d11, src);
-    o.s.inv = __shfl_sync(0xFFFFFFFFu, c.s.inv, src);
-    o.s.x_lo = __shfl_sync(0xFFFFFFFFu, c.s.x_lo, src);
-    o.s.x_hi = __shfl_sync(0xFFFFFFFFu, c.s.x_hi, src);
-    o.s.y_lo = __shfl_sync(0xFFFFFFFFu, c.s.y_lo, src);
-    o.s.y_hi = __shfl_sync(0xFFFFFFFFu, c.s.y_hi, src);
-    o.z0 = __shfl_sync(0xFFFFFFFFu, c.z0, src);
-    if (MODE == kModeTriangles) {
-      o.z1 = __shfl_sync(0xFFFFFFFFu, c.z1, src);
-      o.z2 = __shfl_sync(0xFFFFFFFFu, c.z2, src);
-    } else {
-      o.z1 = o.z2 = 0.f;
+    __syncwarp();
+    if ((int)lane == src) *slot = c;
+    __syncwarp();
+    const Candidate o = *slot;
+    const int bw = o.s.x_hi - o.s.x_lo + 1;
+    if (bw >= 16) {  // wide box: the warp strides along x, row by row
+      for (int y = o.s.y_lo; y <= o.s.y_hi; ++y) offer_span<MODE>(o, km, y, o.s.x_lo + (int)lane, o.s.x_hi, 32, keys, h, w);
+    } else {         // narrow box: 32 / bw' rows at a time (bw' = bw rounded up to a power of two)
+      const int bwp = bw <= 1 ? 1 : (bw <= 2 ? 2 : (bw <= 4 ? 4 : (bw <= 8 ? 8 : 16)));
+      const int rows_per_iter = 32 / bwp;
+      const int dx = (int)lane & (bwp - 1), dy = (int)lane / bwp;
+      for (int y = o.s.y_lo + dy; y <= o.s.y_hi; y += rows_per_iter)
+        if (dx < bw) offer_span<MODE>(o, km, y, o.s.x_lo + dx, o.s.x_lo + dx, 1, keys, h, w);
     }
-    o.id = __shfl_sync(0xFFFFFFFFu, c.id, src);
-    o.n = __shfl_sync(0xFFFFFFFFu, c.n, src);
-    for (int j = lane; j < o.n; j += 32) offer_pixel<MODE>(o, j, keys, h, w);
   }
 }
 
@@ -233,39 +253,38 @@ __global__ void resolve_triangles_kernel(const unsigned long long* __restrict__ 
 }
 
 // Fused-path resolve: 4 pixels per thread, one tri_color gather per covered pixel, every pixel
-// written (uncovered -> 0), so the image needs no clear.  The consumed keys are zeroed in the
-// same pass, which is what the next chunk's scatter expects.  Requires (h*w) % 4 == 0.
+// written (uncovered or stale-epoch key -> 0), so neither the image nor the z-buffer needs a clear.
+// Requires (h*w) % 4 == 0.
 __global__ void __launch_bounds__(256)
-resolve_packed_kernel(unsigned long long* __restrict__ keys, const uint32_t* __restrict__ tri_color,
-                      unsigned char* __restrict__ image, unsigned char* __restrict__ mask, int ntri,
-                      size_t npix) {
+resolve_packed_kernel(const unsigned long long* __restrict__ keys, EpochKey km,
+                      const uint32_t* __restrict__ tri_color, unsigned char* __restrict__ image,
+                      unsigned char* __restrict__ mask, int ntri, size_t npix) {
   const int frame = blockIdx.y;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
   if (q * 4 >= npix) return;
   const size_t base = (size_t)frame * npix + q * 4;
-  const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(keys + base);
-  const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(keys + base + 2);
-  *reinterpret_cast<ulonglong2*>(keys + base) = make_ulonglong2(0ull, 0ull);
-  *reinterpret_cast<ulonglong2*>(keys + base + 2) = make_ulonglong2(0ull, 0ull);
+  const ulonglong2 k01 = __ldcs(reinterpret_cast<const ulonglong2*>(keys + base));
+  const ulonglong2 k23 = __ldcs(reinterpret_cast<const ulonglong2*>(keys + base + 2));
   const unsigned long long k[4] = {k01.x, k01.y, k23.x, k23.y};
   const uint32_t* tc = tri_color + (size_t)frame * ntri;
   uint32_t col[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int t = key_triangle(k[i]);
-    col[i] = (t >= 0) ? __ldg(tc + t) : 0u;
+    const bool live = k[i] >= km.epoch_field;  // written during this chunk
+    const uint32_t t = km.tri_mask - (static_cast<uint32_t>(k[i]) & km.tri_mask);
+    col[i] = live ? __ldg(tc + t) : 0u;
   }
   // 12 bytes of RGB for 4 pixels as three 32-bit words
   const uint32_t w0 = (col[0] & 0xFFFFFFu) | ((col[1] & 0xFFu) << 24);
   const uint32_t w1 = ((col[1] >> 8) & 0xFFFFu) | ((col[2] & 0xFFFFu) << 16);
   const uint32_t w2 = ((col[2] >> 16) & 0xFFu) | ((col[3] & 0xFFFFFFu) << 8);
   uint32_t* out = reinterpret_cast<uint32_t*>(image + base * 3);
-  out[0] = w0;
-  out[1] = w1;
-  out[2] = w2;
+  __stcs(out, w0);
+  __stcs(out + 1, w1);
+  __stcs(out + 2, w2);
   if (mask != nullptr) {
     const uint32_t m = (col[0] >> 24) | ((col[1] >> 24) << 8) | ((col[2] >> 24) << 16) | ((col[3] >> 24) << 24);
-    *reinterpret_cast<uint32_t*>(mask + base) = m;
+    __stcs(reinterpret_cast<uint32_t*>(mask + base), m);
   }
 }
 

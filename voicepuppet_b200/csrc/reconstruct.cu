@@ -152,13 +152,17 @@ int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
 
 // =========================================================================================
 // K2: one CTA per (vertex tile, group of frames).  Per frame:
-//   1. local vertex positions (own + halo) = per-clip base shape (float64) + expression
-//      displacement (float32) -> shared memory, float64;
-//   2. normals of the tile's triangles: edges differenced in float64 (the cancellation-prone
-//      step), cross product in float32 -> shared memory;
-//   3. per own vertex: ring sum in point_buf slot order, normalise, rotate, 9-band SH lighting,
-//      colour, (double) rotation, perspective projection -> one float4 raster record
-//      (x, S - y, -z, rgb bytes) and/or the reference's per-vertex outputs.
+//   1. local vertex positions (own + halo) relative to the tile's first vertex, float32:
+//      (base - origin) is rounded once per tile (|.| ~ tile extent, so its float32 error is ~1e-8
+//      of the mesh scale) and the float32 expression displacement is added -> shared memory.
+//      The edges below are differences of nearby points, so this keeps their cancellation error
+//      at the level of the displacement's own float32 rounding;
+//   2. normals of the tile's triangles (cross products, float32) -> shared memory;
+//   3. per own vertex: ring sum in point_buf slot order (pad slots read a zero entry, like the
+//      zero row the reference appends), normalise, rotate, 9-band SH lighting, colour; position in
+//      float64 (base + displacement), (double) rotation, perspective projection -> one float4
+//      raster record (x, S - y, -z, rgb bytes) and/or the reference's per-vertex outputs.
+// Shared memory is double buffered across frames, so a frame costs two block barriers.
 // =========================================================================================
 struct VertexArgs {
   const TileDesc* tiles;
@@ -174,6 +178,7 @@ struct VertexArgs {
   int nframes;
   int frames_per_block;
   int rotate_first;
+  int has_out;
   double focal, center, image_size, raster_scale;
   float4* vrec;
   size_t vrec_stride;
@@ -181,28 +186,46 @@ struct VertexArgs {
   int nver;
 };
 
-__global__ void __launch_bounds__(kTileV) vertex_tile_kernel(const VertexArgs a) {
-  __shared__ double s_pos[3][kTileLV];
-  __shared__ float s_fn[3][kTileLT];
-  __shared__ FrameParams s_par;
+struct FrameShared {   // per-frame constants staged in shared memory
+  FrameParams par;     // 192 B: rotation (float64), translation, gamma
+  float rot[12];       // rotation as float32
+  float sh[28];        // gamma with the SH band constants (and the 0.8 ambient) folded in: [3][9]
+};
+
+__global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs a) {
+  __shared__ float4 s_pos[2][kTileLV];
+  __shared__ float4 s_fn[kTileLT + 1];
+  __shared__ FrameShared s_frame[2];
   static_assert(sizeof(FrameParams) == 192, "FrameParams layout");
 
   const TileDesc td = a.tiles[blockIdx.x];
   const int tid = threadIdx.x;
+  const int nq_v = (td.nlv + kTileV - 1) / kTileV;  // CTA-uniform trip counts
+  const int nq_t = (td.nlt + kTileV - 1) / kTileV;
 
-  // per-tile constants held in registers across the frame loop
+  // ---- per-tile constants held in registers across the frame loop ------------------------
+  const double ox = __ldg(a.base + 3 * (size_t)td.v_begin), oy = __ldg(a.base + 3 * (size_t)td.v_begin + 1),
+               oz = __ldg(a.base + 3 * (size_t)td.v_begin + 2);
   int gv[3];
-  double bx[3], by[3], bz[3];
+  float rx[3], ry[3], rz[3];
+  double bx = 0.0, by = 0.0, bz = 0.0;  // own vertex, float64
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     const int i = tid + q * kTileV;
-    gv[q] = -1;
-    bx[q] = by[q] = bz[q] = 0.0;
+    gv[q] = td.v_begin;
+    rx[q] = ry[q] = rz[q] = 0.f;
     if (i < td.nlv) {
       gv[q] = (i < td.nv) ? td.v_begin + i : __ldg(a.halo + td.halo_off + i - td.nv);
-      bx[q] = __ldg(a.base + 3 * (size_t)gv[q]);
-      by[q] = __ldg(a.base + 3 * (size_t)gv[q] + 1);
-      bz[q] = __ldg(a.base + 3 * (size_t)gv[q] + 2);
+      const double x = __ldg(a.base + 3 * (size_t)gv[q]), y = __ldg(a.base + 3 * (size_t)gv[q] + 1),
+                   z = __ldg(a.base + 3 * (size_t)gv[q] + 2);
+      rx[q] = (float)(x - ox);
+      ry[q] = (float)(y - oy);
+      rz[q] = (float)(z - oz);
+      if (q == 0) {
+        bx = x;
+        by = y;
+        bz = z;
+      }
     }
   }
   uint32_t lt[4];
@@ -224,89 +247,120 @@ __global__ void __launch_bounds__(kTileV) vertex_tile_kernel(const VertexArgs a)
     }
     orig = __ldg(a.v_int2orig + gv[0]);
   }
+  if (tid == 0) s_fn[kTileLT] = make_float4(0.f, 0.f, 0.f, 0.f);  // what pad slots of the ring read
 
   const int f_begin = blockIdx.y * a.frames_per_block;
   const int f_end = min(a.nframes, f_begin + a.frames_per_block);
-  for (int f = f_begin; f < f_end; ++f) {
-    __syncthreads();  // the previous frame's readers are done with shared memory
-    if (tid < (int)(sizeof(FrameParams) / 4))
-      reinterpret_cast<uint32_t*>(&s_par)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.params + f) + tid);
+
+  // displacement of the first frame (software pipelined: frame f+1 is fetched while f is computed)
+  float dx[3], dy[3], dz[3];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int i = tid + q * kTileV;
-      if (i < td.nlv) {
-        double dx = 0.0, dy = 0.0, dz = 0.0;
-        if (a.disp) {
-          const float* d = a.disp + (size_t)f * a.disp_stride + 3 * (size_t)gv[q];
-          dx = (double)__ldg(d);
-          dy = (double)__ldg(d + 1);
-          dz = (double)__ldg(d + 2);
-        }
-        s_pos[0][i] = bx[q] + dx;
-        s_pos[1][i] = by[q] + dy;
-        s_pos[2][i] = bz[q] + dz;
+  for (int q = 0; q < 3; ++q) dx[q] = dy[q] = dz[q] = 0.f;
+  if (a.disp && f_begin < f_end) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q < nq_v) {
+        const float* d = a.disp + (size_t)f_begin * a.disp_stride + 3 * (size_t)gv[q];
+        dx[q] = __ldg(d);
+        dy[q] = __ldg(d + 1);
+        dz[q] = __ldg(d + 2);
       }
+  }
+
+  for (int f = f_begin; f < f_end; ++f) {
+    const int buf = (f - f_begin) & 1;
+    FrameShared& fs = s_frame[buf];
+    // ---- phase 1: per-frame constants and local positions -> shared memory ----------------
+    if (tid < 48) {
+      reinterpret_cast<uint32_t*>(&fs.par)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.params + f) + tid);
+    } else if (tid < 57) {
+      fs.rot[tid - 48] = (float)__ldg(a.params[f].rot + (tid - 48));
+    } else if (tid >= 64 && tid < 91) {
+      // Illumination_layer (reconstruct_mesh.py:133-153): Y_k = K_k * b_k(n), lit_c = sum_k Y_k gamma'_ck with
+      // gamma' = gamma + 0.8 on band 0; K_k (products of a0..a2, c0..c2, evaluated in float64) folded in here
+      const int k = (tid - 64) % 9;
+      const float kk = (k == 0) ? 0.8862269254527579f
+                                : (k <= 3 ? 1.772453850905516f
+                                          : (k == 6 ? 0.7006239020497412f : (k == 8 ? 1.2135161953473121f : 2.4270323906946243f)));
+      const float sign = (k == 1 || k == 3 || k == 5 || k == 7) ? -1.f : 1.f;
+      const float g = __ldg(a.params[f].gamma + (tid - 64)) + (k == 0 ? 0.8f : 0.f);
+      fs.sh[tid - 64] = sign * kk * g;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q < nq_v) s_pos[buf][tid + q * kTileV] = make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
+    const double own_x = bx + (double)dx[0], own_y = by + (double)dy[0], own_z = bz + (double)dz[0];
+    if (a.disp && f + 1 < f_end) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (q < nq_v) {
+          const float* d = a.disp + (size_t)(f + 1) * a.disp_stride + 3 * (size_t)gv[q];
+          dx[q] = __ldg(d);
+          dy[q] = __ldg(d + 1);
+          dz[q] = __ldg(d + 2);
+        }
     }
     __syncthreads();
+    // ---- phase 2: triangle normals (reconstruct_mesh.py:41-46) ----------------------------
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = tid + q * kTileV;
-      if (j < td.nlt) {
-        const int i1 = lt[q] & 1023u, i2 = (lt[q] >> 10) & 1023u, i3 = (lt[q] >> 20) & 1023u;
-        // e1 = v1 - v2, e2 = v2 - v3 (reconstruct_mesh.py:44-45), differenced in float64
-        const double x2 = s_pos[0][i2], y2 = s_pos[1][i2], z2 = s_pos[2][i2];
-        const float e1x = (float)(s_pos[0][i1] - x2), e1y = (float)(s_pos[1][i1] - y2), e1z = (float)(s_pos[2][i1] - z2);
-        const float e2x = (float)(x2 - s_pos[0][i3]), e2y = (float)(y2 - s_pos[1][i3]), e2z = (float)(z2 - s_pos[2][i3]);
-        s_fn[0][j] = e1y * e2z - e1z * e2y;
-        s_fn[1][j] = e1z * e2x - e1x * e2z;
-        s_fn[2][j] = e1x * e2y - e1y * e2x;
+    for (int q = 0; q < 4; ++q)
+      if (q < nq_t) {
+        const float4 p1 = s_pos[buf][lt[q] & 1023u], p2 = s_pos[buf][(lt[q] >> 10) & 1023u],
+                     p3 = s_pos[buf][(lt[q] >> 20) & 1023u];
+        const float e1x = p1.x - p2.x, e1y = p1.y - p2.y, e1z = p1.z - p2.z;
+        const float e2x = p2.x - p3.x, e2y = p2.y - p3.y, e2z = p2.z - p3.z;
+        s_fn[tid + q * kTileV] = make_float4(e1y * e2z - e1z * e2y, e1z * e2x - e1x * e2z, e1x * e2y - e1y * e2x, 0.f);
       }
-    }
     __syncthreads();
     if (!own) continue;
-
-    // vertex normal: sum of the ring in point_buf slot order (reconstruct_mesh.py:49), normalised (:50)
+    // ---- phase 3: the own vertex ----------------------------------------------------------
     float nx = 0.f, ny = 0.f, nz = 0.f;
     {
       const uint32_t w[4] = {rg.x, rg.y, rg.z, rg.w};
 #pragma unroll
       for (int s = 0; s < VP_RING; ++s) {
-        const uint32_t j = (w[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu;
-        if (j != kRingPad) {
-          nx += s_fn[0][j];
-          ny += s_fn[1][j];
-          nz += s_fn[2][j];
-        }
+        const uint32_t j = min((w[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu, (uint32_t)kTileLT);
+        const float4 fn = s_fn[j];
+        nx += fn.x;
+        ny += fn.y;
+        nz += fn.z;
       }
     }
     {
-      const float len = sqrtf(nx * nx + ny * ny + nz * nz);
-      nx = nx / len;  // 0/0 -> NaN for a vertex without faces, exactly like the reference
-      ny = ny / len;
-      nz = nz / len;
+      const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);  // 0 * inf -> NaN for a vertex without faces
+      nx *= inv;
+      ny *= inv;
+      nz *= inv;
     }
-    const double* R = s_par.rot;
-    // rotated normal (reconstruct_mesh.py:184 / :208) and lighting in float32
-    const float r0 = (float)R[0], r1 = (float)R[1], r2 = (float)R[2], r3 = (float)R[3], r4 = (float)R[4],
-                r5 = (float)R[5], r6 = (float)R[6], r7 = (float)R[7], r8 = (float)R[8];
-    const float nrx = nx * r0 + ny * r3 + nz * r6;
-    const float nry = nx * r1 + ny * r4 + nz * r7;
-    const float nrz = nx * r2 + ny * r5 + nz * r8;
+    // rotated normal (reconstruct_mesh.py:184 / :208), lighting and colour in float32
+    const float* rf = fs.rot;
+    const float nrx = nx * rf[0] + ny * rf[3] + nz * rf[6];
+    const float nry = nx * rf[1] + ny * rf[4] + nz * rf[7];
+    const float nrz = nx * rf[2] + ny * rf[5] + nz * rf[8];
     float lit[3];
-    sh_lighting<float>(s_par.gamma, nrx, nry, nrz, lit);
+    {
+      const float b4 = nrx * nry, b5 = nry * nrz, b6 = 3.f * nrz * nrz - 1.f, b7 = nrx * nrz,
+                  b8 = nrx * nrx - nry * nry;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* g = fs.sh + 9 * c;
+        lit[c] = g[0] + g[1] * nry + g[2] * nrz + g[3] * nrx + g[4] * b4 + g[5] * b5 + g[6] * b6 + g[7] * b7 + g[8] * b8;
+      }
+    }
     const float cr = lit[0] * tr, cg = lit[1] * tg, cb = lit[2] * tb;
 
     // geometry in float64
-    double sx = s_pos[0][tid], sy = s_pos[1][tid], sz = s_pos[2][tid];
+    const double* R = fs.par.rot;
+    double sx = own_x, sy = own_y, sz = own_z;
     if (a.rotate_first) {  // Reconstruction_rotation rotates the shape before projecting it (:211)
-      double ox, oy, oz;
-      rotate_row(R, sx, sy, sz, ox, oy, oz);
-      sx = ox;
-      sy = oy;
-      sz = oz;
+      double tx, ty, tz;
+      rotate_row(R, sx, sy, sz, tx, ty, tz);
+      sx = tx;
+      sy = ty;
+      sz = tz;
     }
     double px, py, zb;
-    project(R, s_par.trans, a.focal, a.center, sx, sy, sz, px, py, zb);
+    project(R, fs.par.trans, a.focal, a.center, sx, sy, sz, px, py, zb);
     const double pyf = a.image_size - py;  // reconstruct_mesh.py:187 / :215
 
     if (a.vrec) {
@@ -315,27 +369,29 @@ __global__ void __launch_bounds__(kTileV) vertex_tile_kernel(const VertexArgs a)
       a.vrec[(size_t)f * a.vrec_stride + gv[0]] =
           make_float4((float)(px * a.raster_scale), (float)(pyf * a.raster_scale), (float)zb, __uint_as_float(rgba));
     }
-    const size_t o = (size_t)f * a.nver + orig;
-    if (a.out.shape) {
-      a.out.shape[3 * o] = sx;
-      a.out.shape[3 * o + 1] = sy;
-      a.out.shape[3 * o + 2] = sz;
+    if (a.has_out) {
+      const size_t o = (size_t)f * a.nver + orig;
+      if (a.out.shape) {
+        a.out.shape[3 * o] = sx;
+        a.out.shape[3 * o + 1] = sy;
+        a.out.shape[3 * o + 2] = sz;
+      }
+      if (a.out.norm) {
+        a.out.norm[3 * o] = nx;
+        a.out.norm[3 * o + 1] = ny;
+        a.out.norm[3 * o + 2] = nz;
+      }
+      if (a.out.color) {
+        a.out.color[3 * o] = cr;
+        a.out.color[3 * o + 1] = cg;
+        a.out.color[3 * o + 2] = cb;
+      }
+      if (a.out.proj) {
+        a.out.proj[2 * o] = px;
+        a.out.proj[2 * o + 1] = a.out.flip_y ? pyf : py;
+      }
+      if (a.out.zbuf) a.out.zbuf[o] = zb;
     }
-    if (a.out.norm) {
-      a.out.norm[3 * o] = nx;
-      a.out.norm[3 * o + 1] = ny;
-      a.out.norm[3 * o + 2] = nz;
-    }
-    if (a.out.color) {
-      a.out.color[3 * o] = cr;
-      a.out.color[3 * o + 1] = cg;
-      a.out.color[3 * o + 2] = cb;
-    }
-    if (a.out.proj) {
-      a.out.proj[2 * o] = px;
-      a.out.proj[2 * o + 1] = a.out.flip_y ? pyf : py;
-    }
-    if (a.out.zbuf) a.out.zbuf[o] = zb;
   }
 }
 
@@ -357,6 +413,7 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.nframes = nframes;
   a.frames_per_block = nframes >= 16 ? 4 : 1;
   a.rotate_first = rotate_first;
+  a.has_out = (out.shape || out.norm || out.color || out.proj || out.zbuf) ? 1 : 0;
   a.focal = focal;
   a.center = center;
   a.image_size = image_size;

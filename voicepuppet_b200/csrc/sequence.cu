@@ -86,19 +86,19 @@ int reserve_chunk(vp_model* m, int chunk, int group, int res) {
   const size_t key_bytes = (size_t)chunk * npix * sizeof(unsigned long long);
   void* before = m->ws_keys.ptr;
   VP_CUDA(m->ws_keys.reserve(key_bytes, m->device));
-  if (m->ws_keys.ptr != before) m->keys_clean_bytes = 0;
+  if (m->ws_keys.ptr != before) m->key_epoch = 0;
   return VP_OK;
 }
 
 // one chunk, everything on the device, nothing synchronised; disp_dev holds this chunk's displacements
 int render_chunk(vp_model* m, int n, const float* disp_dev, const FrameParams* params_dev, int rotate_first, int res,
                  unsigned char* image_dev, unsigned char* mask_dev, cudaStream_t st, Profiler& prof) {
-  const size_t npix = (size_t)res * res;
-  const size_t key_bytes = (size_t)n * npix * sizeof(unsigned long long);
-  if (m->keys_clean_bytes < key_bytes) {  // the resolve pass leaves the keys it consumed zeroed
+  // every chunk gets a fresh epoch; stale keys lose every atomicMax and read as background
+  if (m->key_epoch == 0 || m->key_epoch >= epoch_limit(m->ntri)) {
     VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
-    m->keys_clean_bytes = m->ws_keys.cap;
+    m->key_epoch = 0;
   }
+  const uint32_t epoch = ++m->key_epoch;
   float4* vrec = m->ws_vrec.as<float4>();
   unsigned long long* keys = m->ws_keys.as<unsigned long long>();
   uint32_t* tricol = m->ws_tricol.as<uint32_t>();
@@ -108,10 +108,10 @@ int render_chunk(vp_model* m, int n, const float* disp_dev, const FrameParams* p
                        st));
   prof.end();
   prof.begin(kProfScatter);
-  VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, n, m->ntri, res, res, st));
+  VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, epoch, n, m->ntri, res, res, st));
   prof.end();
   prof.begin(kProfResolve);
-  VP_TRY(launch_resolve_packed(keys, tricol, image_dev, mask_dev, n, m->ntri, res, res, st));
+  VP_TRY(launch_resolve_packed(keys, tricol, epoch, image_dev, mask_dev, n, m->ntri, res, res, st));
   prof.end();
   return VP_OK;
 }
@@ -164,7 +164,7 @@ extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_
                       image_dev + (size_t)t0 * npix * 3, face_mask_dev ? face_mask_dev + (size_t)t0 * npix : nullptr,
                       st, prof);
   }
-  if (rc != VP_OK) m->keys_clean_bytes = 0;
+  if (rc != VP_OK) m->key_epoch = 0;
   prof.finish();
   return rc;
 }
@@ -253,7 +253,7 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
       rc = VP_ERR_CUDA;
     }
   }
-  if (rc != VP_OK) m->keys_clean_bytes = 0;
+  if (rc != VP_OK) m->key_epoch = 0;
   prof.finish();
   return rc;
 }

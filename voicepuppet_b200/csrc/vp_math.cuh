@@ -183,8 +183,9 @@ VP_HD void project(const double* R, const float* t, double focal, double center,
   ry += static_cast<double>(t[1]);
   rz += static_cast<double>(t[2]);
   const double zc = 10.0 - rz;  // reverse_z then + camera_pos
-  px = (focal * rx + center * zc) / zc;
-  py = (focal * ry + center * zc) / zc;
+  const double inv = 1.0 / zc;  // (f*x + c*z) / z with one reciprocal: differs from the division by <= 1 ulp of float64
+  px = (focal * rx + center * zc) * inv;
+  py = (focal * ry + center * zc) * inv;
   zbuf = -zc;
 }
 

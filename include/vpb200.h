@@ -204,6 +204,16 @@ int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev,
                            const vp_frame_params* params_dev, int rotate_shape_first, int res,
                            unsigned char* image_dev, unsigned char* face_mask_dev, void* stream);
 
+/* The expression contraction alone (device pointers, asynchronous on `stream`):
+ * disp_dev[t][r] = sum_k exBase[r][k] * ex_dev[t][k], r in the library's internal row order
+ * (3 * internal vertex + axis), vp_model_rows_pad() floats per frame. */
+int vp_basis_dev(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, void* stream);
+int vp_model_rows_pad(const vp_model* m);
+/* Diagnostics: one tcgen05 basis launch (nframes <= 128) that also writes a clock64() timeline of
+ * CTA 0 to trace_dev[256] (4 roles x 16 tiles x 4 marks). */
+int vp_debug_basis_trace(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
+                         long long* trace_dev, void* stream);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 unsigned long long vp_launch_count(void);
 

@@ -1,0 +1,26 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from voicepuppet_b200 import _lib, synthetic
+from voicepuppet_b200.model import DeviceModel
+lib = _lib.lib(); dev = torch.device('cuda', 0)
+model = synthetic.cached_model(); dm = DeviceModel.of(model)
+rows_pad = lib.vp_model_rows_pad(dm.handle)
+st = torch.cuda.current_stream(dev).cuda_stream
+for t in (16, 75):
+  ex = torch.randn(t, 64, device=dev); disp = torch.empty(t, rows_pad, device=dev)
+  trace = torch.zeros(256, dtype=torch.int64, device=dev)
+  for _ in range(3):
+    _lib.check(lib.vp_debug_basis_trace(dm.handle, ex.data_ptr(), disp.data_ptr(), t, trace.data_ptr(), st))
+  torch.cuda.synchronize()
+  tr = trace.cpu().numpy().reshape(4, 16, 4)
+  t0 = tr[tr > 0].min()
+  print('T=%d (clock cycles relative to the first mark)' % t)
+  names = ['producer: loop-top, afree-ok, issued', 'mma: loop-top, split-ok, accfree-ok, committed',
+           'worker: loop-top, full-ok, split-done, arrived', 'epilogue: start, mma-ok, done']
+  for r in range(4):
+    print(' ', names[r])
+    for it in range(7):
+      row = tr[r, it]
+      if row.max() > 0:
+        print('    it=%d ' % it + ' '.join('%7d' % (x - t0) if x > 0 else '      -' for x in row))

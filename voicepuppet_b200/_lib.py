@@ -80,6 +80,9 @@ SIGNATURES = {
     'vp_projection': (_i, [_i, _i, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp]),
     'vp_render_sequence': (_i, [_vp, ctypes.POINTER(VpFrames), _i, _vp, _vp, _i, _vp]),
     'vp_render_sequence_dev': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'vp_basis_dev': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'vp_model_rows_pad': (_i, [_vp]),
+    'vp_debug_basis_trace': (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     'vp_launch_count': (ctypes.c_ulonglong, []),
     'vp_set_profiling': (_i, [_vp, _i]),
     'vp_get_profile': (_i, [_vp, ctypes.c_char_p, _i, _vp, _i]),

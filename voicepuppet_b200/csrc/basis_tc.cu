@@ -1,19 +1,27 @@
 // K1, tensor-core flavour: disp[t][r] = sum_k exb[r][k] * ex[t][k] as a tcgen05 3xTF32 GEMM.
 // (reference: the expression einsum of Shape_formation, utils/reconstruct_mesh.py:21-22)
 //
-// GEMM view: D[M = 128 basis rows][N = frames] += A[M][K = 64] * B[N][K]^T, both operands K-major.
-//   * A tile (128 x 64 fp32 = 32 KB) arrives by two TMA tensor loads (one per 32-float K half) in
-//     the canonical 128-byte-swizzled K-major layout the UMMA shared-memory descriptor expects;
-//   * 3xTF32: every fp32 operand x is split in shared memory into hi = tf32(x) and lo = tf32(x - hi);
-//     D = A_lo*B_hi + A_hi*B_lo + A_hi*B_hi with FP32 accumulation in TMEM recovers ~fp32 accuracy
-//     (the dropped lo*lo term is 2^-22 relative).  The basis is read from HBM once, as fp32;
-//   * one elected thread issues the 24 tcgen05.mma (3 products x 8 K-steps of 8) per frame tile and
-//     commits them to an mbarrier; the four warps then drain their TMEM lane quarter with
-//     tcgen05.ld (32 lanes x 16 columns) and store frame-major, 128 contiguous bytes per warp store.
+// GEMM view: D[M = 128 basis rows][N = frames <= 128] = A[M][K = 64] * B[N][K]^T, operands K-major.
+// Persistent, warp-specialised kernel, one CTA per SM, each CTA walks basis row tiles m, m+grid, ...:
+//   warp 0 (one lane)   TMA producer: two tensor loads per tile (one per 32-float K half) land the
+//                       128 x 64 fp32 tile (32 KB) in the canonical 128-byte-swizzled K-major layout
+//                       the UMMA shared-memory descriptor expects; 3-stage ring, plus L2 prefetches
+//                       (cp.async.bulk.prefetch.tensor) four tiles ahead
+//   warps 10-17         3xTF32 split of the landed tile: the tensor core reads the top 19 bits of each fp32
+//                       container, so the landed tile IS the "hi" operand; lo = x - trunc_tf32(x) goes
+//                       into a second tile (elementwise, so the swizzle is kept); 2-stage ring
+//   warp 1 (one lane)   issues 24 tcgen05.mma per tile: (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi) x 8 K-steps
+//                       of 8, FP32 accumulation in TMEM (2 accumulators of 128 columns), and commits
+//                       them to the mbarriers that free the A stage and release the epilogue
+//   warps 2-9           epilogue, two warps per TMEM lane quarter: tcgen05.ld (32 rows x 16 frames per
+//                       load), frame-major stores, 128 contiguous bytes per warp store
+// The frame coefficients (B) are split once per CTA.  The dropped lo*lo term is 2^-22 relative, so the
+// result has fp32-grade accuracy; the basis is read from HBM once, as fp32.
 // The contraction is HBM-bound (K = 64: at most 32 flop/B); tensor cores are used to get the FP32
 // SIMT pipe out of the way, not because the math is heavy.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "launch.h"
@@ -23,32 +31,37 @@ namespace vp {
 
 namespace {
 
-constexpr int kTcM = 128;                 // basis rows per CTA (UMMA M)
-constexpr int kTcN = 64;                  // frames per accumulator tile (TMEM columns)
-constexpr int kHalfA = kTcM * 128;        // bytes of one K-half (32 floats) of the A tile
-constexpr int kHalfB = kTcN * 128;
+constexpr int kTcM = 128;                 // basis rows per tile (UMMA M)
+constexpr int kTcN = 128;                 // max frames per launch (UMMA N, TMEM columns per accumulator)
+constexpr int kStagesA = 3;               // TMA ring of fp32 A tiles (become the "hi" operand in place)
+constexpr int kStagesL = 2;               // "lo" tiles and TMEM accumulators
+constexpr int kHalfA = kTcM * 128;        // bytes of one K-half (32 floats) of an A tile
+constexpr int kTileA = 2 * kHalfA;        // 32 KB
 constexpr int kOffAhi = 0;
-constexpr int kOffAlo = 2 * kHalfA;
-constexpr int kOffBhi = 4 * kHalfA;
-constexpr int kOffBlo = 4 * kHalfA + 2 * kHalfB;
-constexpr int kOffBar = 4 * kHalfA + 4 * kHalfB;
-constexpr int kTcSmem = kOffBar + 64 + 1024;  // + alignment slack
+constexpr int kOffAlo = kStagesA * kTileA;
+constexpr int kOffB = kOffAlo + kStagesL * kTileA;     // B hi/lo tiles (1024-byte aligned; size depends on the frame
+                                                       // count), then the barriers
+// warp roles: 0 = TMA producer, 1 = MMA issuer, 2-9 = epilogue (two warps per TMEM lane quarter),
+// 10-17 = operand split
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpEpi0 = 2, kWarpSplit0 = 10;
+constexpr int kEpiThreads = 256, kSplitThreads = 256;
+constexpr int kTcThreads = (kWarpSplit0 * 32) + kSplitThreads;  // 576
+constexpr int kPrefetchTiles = 4;         // L2 prefetch distance of the TMA producer, in tiles
+constexpr uint32_t kTf32Mask = 0xFFFFE000u;
 
-__device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+inline int tc_smem_bytes(int n_mma) { return kOffB + 2 * n_mma * 256 + 128; }
 
+// 3xTF32 split by truncation: hi keeps the 19 bits the tensor core reads, lo = x - hi is exact in fp32
+// (|lo| < 2^-10 |x|) and is truncated to its own top 19 bits by the tensor core: 2^-21 relative overall.
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-  hi.x = tf32_round(v.x);
-  hi.y = tf32_round(v.y);
-  hi.z = tf32_round(v.z);
-  hi.w = tf32_round(v.w);
-  lo.x = tf32_round(v.x - hi.x);
-  lo.y = tf32_round(v.y - hi.y);
-  lo.z = tf32_round(v.z - hi.z);
-  lo.w = tf32_round(v.w - hi.w);
+  hi.x = __uint_as_float(__float_as_uint(v.x) & kTf32Mask);
+  hi.y = __uint_as_float(__float_as_uint(v.y) & kTf32Mask);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & kTf32Mask);
+  hi.w = __uint_as_float(__float_as_uint(v.w) & kTf32Mask);
+  lo.x = v.x - hi.x;
+  lo.y = v.y - hi.y;
+  lo.z = v.z - hi.z;
+  lo.w = v.w - hi.w;
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
@@ -64,109 +77,213 @@ __device__ __forceinline__ uint32_t instr_desc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void tma_prefetch_2d(const void* tensor_map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tensor_map), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
 basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ ex, float* __restrict__ disp,
-                int nframes, int rows_pad) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* bar_mma = bar_tma + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tma + 2);
+                int nframes, int rows_pad, int ntiles, long long* __restrict__ trace) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // optional per-role timeline of CTA 0 (diagnostics): trace[role * 64 + it * 4 + k] = clock64()
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+#define VP_TRACE(role, it, k) do { if (tracing && (it) < 16) trace[(role) * 64 + (it) * 4 + (k)] = clock64(); } while (0)
+  const int n_mma = (nframes + 15) & ~15;  // <= kTcN
+  const int half_b = n_mma * 128;          // bytes of one K-half of a B tile
+  uint8_t* smem_bhi = smem + kOffB;
+  uint8_t* smem_blo = smem_bhi + 2 * half_b;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_blo + 2 * half_b);  // [3] TMA landed
+  uint64_t* bar_afree = bar_full + kStagesA;                         // [3] MMAs that read the A stage completed
+  uint64_t* bar_split = bar_afree + kStagesA;                        // [2] hi/lo tiles ready for the MMA
+  uint64_t* bar_mma = bar_split + kStagesL;                          // [2] accumulator complete (and lo tile free)
+  uint64_t* bar_accfree = bar_mma + kStagesL;                        // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfree + kStagesL);
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int row0 = blockIdx.x * kTcM;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
+  const int lane = tid & 31;
 
   if (tid == 0) {
+    if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
     ptx::prefetch_tensormap(&tmap_a);
-    ptx::mbar_init(bar_tma, 1);
-    ptx::mbar_init(bar_mma, 1);
+    for (int s = 0; s < kStagesA; ++s) {
+      ptx::mbar_init(bar_full + s, 1);
+      ptx::mbar_init(bar_afree + s, 1);
+    }
+    for (int s = 0; s < kStagesL; ++s) {
+      ptx::mbar_init(bar_split + s, kSplitThreads);
+      ptx::mbar_init(bar_mma + s, 1);
+      ptx::mbar_init(bar_accfree + s, kEpiThreads);
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, kTcN);
+  if (warp == kWarpMma) {
+    ptx::tmem_alloc(tmem_slot, kStagesL * kTcN);
     ptx::tmem_relinquish();
+  }
+  if (warp >= kWarpSplit0) {
+    // frame coefficients -> hi / lo tiles in the swizzled K-major layout: row n (frame), 16-byte chunk
+    // c of K-half h lives at h * half_b + (n / 8) * 1024 + (n % 8) * 128 + ((c ^ (n % 8)) * 16)
+    for (int q = tid - kWarpSplit0 * 32; q < n_mma * 16; q += kSplitThreads) {
+      const int n = q >> 4, c16 = q & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < nframes) v = __ldg(reinterpret_cast<const float4*>(ex + (size_t)n * VP_N_EX) + c16);
+      float4 h, l;
+      split4(v, h, l);
+      const int off = (c16 >> 3) * half_b + (n >> 3) * 1024 + (n & 7) * 128 + (((c16 & 7) ^ (n & 7)) << 4);
+      *reinterpret_cast<float4*>(smem_bhi + off) = h;
+      *reinterpret_cast<float4*>(smem_blo + off) = l;
+    }
+    ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int first = blockIdx.x, step = gridDim.x;
 
-  if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar_tma, 2 * kHalfA);
-    ptx::tma_load_2d(smem + kOffAhi, &tmap_a, 0, row0, bar_tma);
-    ptx::tma_load_2d(smem + kOffAhi + kHalfA, &tmap_a, 32, row0, bar_tma);
-  }
-  ptx::mbar_wait(bar_tma, 0);
-
-  // split the A tile in place (elementwise, so the swizzled layout is preserved)
-  {
-    float4* hi4 = reinterpret_cast<float4*>(smem + kOffAhi);
-    float4* lo4 = reinterpret_cast<float4*>(smem + kOffAlo);
-#pragma unroll 4
-    for (int i = tid; i < 2 * kHalfA / 16; i += 128) {
-      float4 h, l;
-      split4(hi4[i], h, l);
-      hi4[i] = h;
-      lo4[i] = l;
-    }
-  }
-
-  const uint32_t a_hi = ptx::smem_u32(smem + kOffAhi), a_lo = ptx::smem_u32(smem + kOffAlo);
-  const uint32_t b_hi = ptx::smem_u32(smem + kOffBhi), b_lo = ptx::smem_u32(smem + kOffBlo);
-  uint32_t phase = 0;
-  for (int t0 = 0; t0 < nframes; t0 += kTcN) {
-    const int nt = min(kTcN, nframes - t0);
-    const int n_mma = (nt + 15) & ~15;
-    // frame coefficients -> hi / lo tiles in the same swizzled K-major layout: row n (frame), 16-byte
-    // chunk c of K-half h lives at h * kHalfB + (n / 8) * 1024 + (n % 8) * 128 + ((c ^ (n % 8)) * 16)
-    for (int q = tid; q < n_mma * 16; q += 128) {
-      const int n = q >> 4, c16 = q & 15;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n < nt) v = __ldg(reinterpret_cast<const float4*>(ex + (size_t)(t0 + n) * VP_N_EX) + c16);
-      float4 h, l;
-      split4(v, h, l);
-      const int off = (c16 >> 3) * kHalfB + (n >> 3) * 1024 + (n & 7) * 128 + (((c16 & 7) ^ (n & 7)) << 4);
-      *reinterpret_cast<float4*>(smem + kOffBhi + off) = h;
-      *reinterpret_cast<float4*>(smem + kOffBlo + off) = l;
-    }
-    ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    ptx::tc_fence_before();    // and the previous tile's tcgen05.ld are ordered before the next MMA
-    __syncthreads();
-    if (tid == 0) {
-      ptx::tc_fence_after();
-      const uint32_t idesc = instr_desc_tf32(kTcM, n_mma);
-      uint32_t acc = 0;
-#pragma unroll
-      for (int part = 0; part < 3; ++part) {  // small terms first
-        const uint32_t a_base = (part == 0) ? a_lo : a_hi;
-        const uint32_t b_base = (part == 1) ? b_lo : b_hi;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // K = 8 per instruction; 4 steps per 128-byte swizzle atom
-          const uint32_t koff_a = (ks >> 2) * kHalfA + (ks & 3) * 32;
-          const uint32_t koff_b = (ks >> 2) * kHalfB + (ks & 3) * 32;
-          ptx::mma_tf32_ss(tmem_base, smem_desc_sw128(a_base + koff_a), smem_desc_sw128(b_base + koff_b), idesc, acc);
-          acc = 1;
+  if (warp == kWarpTma) {
+    // ===== TMA producer (whole warp loops, one elected lane issues) =====
+    if (elect_one()) {
+      for (int p = 0; p < kPrefetchTiles; ++p) {
+        const int mp = first + p * step;
+        if (mp < ntiles) {
+          tma_prefetch_2d(&tmap_a, 0, mp * kTcM);
+          tma_prefetch_2d(&tmap_a, 32, mp * kTcM);
         }
       }
-      ptx::tc_commit(bar_mma);
     }
-    ptx::mbar_wait(bar_mma, phase);
-    phase ^= 1;
-    ptx::tc_fence_after();
-    // epilogue: warp w owns TMEM lanes 32w..32w+31 (= basis rows), columns = frames
-    float* out = disp + (size_t)t0 * rows_pad + row0 + warp * 32 + lane;
-    for (int c0 = 0; c0 < n_mma; c0 += 16) {
-      uint32_t r[16];
-      ptx::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-      ptx::tmem_ld_wait();
+    int it = 0;
+    for (int m = first; m < ntiles; m += step, ++it) {
+      const int s = it % kStagesA;
+      if (it >= kStagesA) ptx::mbar_wait(bar_afree + s, ((it / kStagesA) - 1) & 1);
+      if (elect_one()) {
+        const int mp = m + kPrefetchTiles * step;
+        if (mp < ntiles) {
+          tma_prefetch_2d(&tmap_a, 0, mp * kTcM);
+          tma_prefetch_2d(&tmap_a, 32, mp * kTcM);
+        }
+        uint8_t* dst = smem + kOffAhi + s * kTileA;
+        ptx::mbar_arrive_expect_tx(bar_full + s, kTileA);
+        ptx::tma_load_2d(dst, &tmap_a, 0, m * kTcM, bar_full + s);
+        ptx::tma_load_2d(dst + kHalfA, &tmap_a, 32, m * kTcM, bar_full + s);
+        VP_TRACE(0, it, 2);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kWarpMma) {
+    // ===== MMA issuer (whole warp loops, one elected lane issues) =====
+    const uint32_t idesc = instr_desc_tf32(kTcM, n_mma);
+    const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);  // SBO, version, SWIZZLE_128B
+    const uint32_t smem_base = ptx::smem_u32(smem);
+    const uint32_t b_hi = (smem_base + kOffB) >> 4, b_lo = (smem_base + kOffB + 2 * half_b) >> 4;
+    const uint32_t half_b16 = half_b >> 4;
+    int it = 0;
+    for (int m = first; m < ntiles; m += step, ++it) {
+      const int sa = it % kStagesA, sl = it & 1;
+      VP_TRACE(1, it, 0);
+      ptx::mbar_wait(bar_split + sl, (it >> 1) & 1);
+      VP_TRACE(1, it, 1);
+      if (it >= kStagesL) ptx::mbar_wait(bar_accfree + sl, ((it >> 1) - 1) & 1);
+      VP_TRACE(1, it, 2);
+      ptx::tc_fence_after();
+      const uint32_t a_hi = (smem_base + kOffAhi + sa * kTileA) >> 4, a_lo = (smem_base + kOffAlo + sl * kTileA) >> 4;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(sl * kTcN);
+      if (elect_one()) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (c0 + j < nt) out[(size_t)(c0 + j) * rows_pad] = __uint_as_float(r[j]);
+        for (int part = 0; part < 3; ++part) {  // small terms first
+          const uint32_t a_base = (part == 0) ? a_lo : a_hi;
+          const uint32_t b_base = (part == 1) ? b_lo : b_hi;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {  // K = 8 per instruction; 4 steps per 128-byte swizzle atom
+            const uint32_t ka = a_base + (ks >> 2) * (kHalfA >> 4) + (ks & 3) * 2;
+            const uint32_t kb = b_base + (ks >> 2) * half_b16 + (ks & 3) * 2;
+            ptx::mma_tf32_ss(d_tmem, desc_hi | (1ull << 16) | (uint64_t)(ka & 0x3FFFu),
+                             desc_hi | (1ull << 16) | (uint64_t)(kb & 0x3FFFu), idesc, (part | ks) != 0);
+          }
+        }
+        ptx::tc_commit(bar_mma + sl);
+        ptx::tc_commit(bar_afree + sa);
+      }
+      __syncwarp();
+      VP_TRACE(1, it, 3);
+    }
+  } else if (warp < kWarpSplit0) {
+    // ===== epilogue warps: drain accumulator `it` (TMEM -> registers -> global, frame-major) =====
+    const int ew = warp - kWarpEpi0;     // 0..7
+    const int quarter = warp & 3;        // TMEM lanes this warp may read: 32 * (warp % 4) ..
+    const int group = ew >> 2;           // two warps per lane quarter alternate over 16-column chunks
+    int it = 0;
+    for (int m = first; m < ntiles; m += step, ++it) {
+      const int sl = it & 1;
+      if (ew == 0 && lane == 0) VP_TRACE(3, it, 0);
+      ptx::mbar_wait(bar_mma + sl, (it >> 1) & 1);
+      if (ew == 0 && lane == 0) VP_TRACE(3, it, 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * kTcN);
+      float* out = disp + (size_t)m * kTcM + quarter * 32 + lane;
+      for (int c0 = group * 16; c0 < n_mma; c0 += 32) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
+        float* o = out + (size_t)c0 * rows_pad;
+        if (c0 + 16 <= nframes) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < nframes) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(bar_accfree + sl);
+      if (ew == 0 && lane == 0) VP_TRACE(3, it, 2);
+    }
+  } else {
+    // ===== split warps: hi / lo tiles of A tile `it` =====
+    const int wt = tid - kWarpSplit0 * 32;  // 0..255
+    int it = 0;
+    for (int m = first; m < ntiles; m += step, ++it) {
+      const int sa = it % kStagesA, sl = it & 1;
+      if (wt == 0) VP_TRACE(2, it, 0);
+      if (it >= kStagesL) ptx::mbar_wait(bar_mma + sl, ((it >> 1) - 1) & 1);  // MMAs of tile it-2 no longer read lo[sl]
+      ptx::mbar_wait(bar_full + sa, (it / kStagesA) & 1);
+      if (wt == 0) VP_TRACE(2, it, 1);
+      float4* hi4 = reinterpret_cast<float4*>(smem + kOffAhi + sa * kTileA);
+      float4* lo4 = reinterpret_cast<float4*>(smem + kOffAlo + sl * kTileA);
+      float4 v[kTileA / 16 / kSplitThreads];
+#pragma unroll
+      for (int u = 0; u < kTileA / 16 / kSplitThreads; ++u) v[u] = hi4[wt + u * kSplitThreads];
+#pragma unroll
+      for (int u = 0; u < kTileA / 16 / kSplitThreads; ++u) {
+        float4 h, l;
+        split4(v[u], h, l);
+#ifdef VP_TC_HI_WRITEBACK  // not needed: kind::tf32 reads the top 19 bits of the fp32 container (verified bit-identical)
+        hi4[wt + u * kSplitThreads] = h;
+#endif
+        lo4[wt + u * kSplitThreads] = l;
+      }
+      if (wt == 0) VP_TRACE(2, it, 2);
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(bar_split + sl);
+      if (wt == 0) VP_TRACE(2, it, 3);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTcN);
+  if (warp == kWarpMma) ptx::tmem_dealloc(tmem_base, kStagesL * kTcN);
+#undef VP_TRACE
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -211,18 +328,30 @@ int basis_tc_prepare(vp_model* m) {
     return VP_ERR_CUDA;
   }
   std::memcpy(m->tmap_exb, &map, sizeof(map));
-  VP_CUDA(cudaFuncSetAttribute(basis_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem));
+  VP_CUDA(cudaFuncSetAttribute(basis_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcN)));
   m->have_tmap = true;
   return VP_OK;
 }
 
-int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st) {
+// nframes <= kTcN per launch: longer batches are cut into launches of 128 frames (the basis then
+// comes from L2 for every launch after the first).
+int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st,
+                    long long* trace_dev) {
   if (nframes == 0) return VP_OK;
   VP_REQUIRE(m->have_tmap, "tensor map not prepared");
   CUtensorMap map;
   std::memcpy(&map, m->tmap_exb, sizeof(map));
-  basis_tc_kernel<<<m->rows_pad / kTcM, 128, kTcSmem, st>>>(map, ex_dev, disp_dev, nframes, m->rows_pad);
-  VP_LAUNCH_CHECK();
+  const int ntiles = m->rows_pad / kTcM;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  const int grid = std::min(ntiles, sms);
+  for (int t0 = 0; t0 < nframes; t0 += kTcN) {
+    const int n = std::min(kTcN, nframes - t0);
+    basis_tc_kernel<<<grid, kTcThreads, tc_smem_bytes((n + 15) & ~15), st>>>(map, ex_dev + (size_t)t0 * VP_N_EX,
+                                                       disp_dev + (size_t)t0 * m->rows_pad, n, m->rows_pad, ntiles,
+                                                       trace_dev);
+    VP_LAUNCH_CHECK();
+  }
   return VP_OK;
 }
 

@@ -127,7 +127,8 @@ int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
 int launch_basis_simt(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st);
 // tcgen05 3xTF32 flavour (basis_tc.cu); basis_tc_prepare builds the TMA descriptor once per model
 int basis_tc_prepare(vp_model* m);
-int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st);
+int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st,
+                    long long* trace_dev = nullptr);
 enum BasisMode { kBasisAuto = 0, kBasisSimt = 1, kBasisTensor = 2 };
 constexpr int kBasisTensorMinFrames = 16;  // below this the frame batch is a GEMV, not a dense contraction
 // disp_dev may be NULL (no expression displacement).  vrec_dev may be NULL (no raster records).

@@ -258,6 +258,28 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
   return rc;
 }
 
+// The expression contraction on its own, device pointers, nothing synchronised:
+// disp[t][r] = sum_k exBase[r][k] * ex[t][k] in the library's internal row order (r = 3 * internal
+// vertex + axis, vp_model_rows_pad() floats per frame).  Used by the micro-benchmarks and tests.
+extern "C" int vp_basis_dev(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, void* stream) {
+  VP_REQUIRE(m != nullptr && ex_dev != nullptr && disp_dev != nullptr && nframes >= 0, "bad argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  VP_CUDA(cudaSetDevice(m->device));
+  return launch_basis(m, ex_dev, disp_dev, nframes, static_cast<cudaStream_t>(stream));
+}
+
+// Diagnostics: one tcgen05 basis launch with a clock64() timeline of CTA 0 written to trace_dev[256]
+// (4 roles x 16 tiles x 4 marks; see VP_TRACE in basis_tc.cu).
+extern "C" int vp_debug_basis_trace(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
+                                    long long* trace_dev, void* stream) {
+  VP_REQUIRE(m != nullptr && ex_dev && disp_dev && trace_dev && nframes > 0 && nframes <= 128, "bad argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  VP_CUDA(cudaSetDevice(m->device));
+  return launch_basis_tc(m, ex_dev, disp_dev, nframes, static_cast<cudaStream_t>(stream), trace_dev);
+}
+
+extern "C" int vp_model_rows_pad(const vp_model* m) { return m ? m->rows_pad : -1; }
+
 extern "C" int vp_set_profiling(vp_model* m, int enabled) {
   VP_REQUIRE(m != nullptr, "null model");
   std::lock_guard<std::mutex> lock(m->mu);

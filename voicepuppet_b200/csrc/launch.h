@@ -22,8 +22,8 @@ uint32_t epoch_limit(int ntri);
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
                           unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
                           int w, cudaStream_t st);
-int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, uint32_t epoch,
-                          unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
+int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, const int* t_orig2int,
+                          uint32_t epoch, unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
                           cudaStream_t st);
 
 // ---- vertex-tile topology (topology.cpp builds it, reconstruct.cu consumes it) ----------
@@ -88,6 +88,7 @@ struct vp_model {
   bool idb64 = false, texb64 = false;
   int4* tri = nullptr;          // [ntri] internal vertex ids + original triangle index
   int* v_int2orig_dev = nullptr;
+  int* t_orig2int_dev = nullptr; // [ntri] original triangle index -> internal (rasterizer) order
   // device: vertex tiles
   int ntiles = 0;
   vp::TileDesc* tiles = nullptr;
@@ -104,7 +105,7 @@ struct vp_model {
   bool have_base = false, have_tex = false;
 
   // workspaces (grow only)
-  vp::DevBuf ws_ex, ws_params, ws_disp, ws_vrec, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
+  vp::DevBuf ws_fshared, ws_ex, ws_params, ws_disp, ws_vrec, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
   uint32_t key_epoch = 0;       // epoch of the last chunk rendered into ws_keys (0 = buffer must be cleared)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};

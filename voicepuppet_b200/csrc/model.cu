@@ -54,6 +54,7 @@ void free_model(vp_model* m) {
   cudaFree(m->meantex);
   cudaFree(m->tri);
   cudaFree(m->v_int2orig_dev);
+  cudaFree(m->t_orig2int_dev);
   cudaFree(m->tiles);
   cudaFree(m->ltri);
   cudaFree(m->halo);
@@ -61,6 +62,7 @@ void free_model(vp_model* m) {
   cudaFree(m->base);
   cudaFree(m->tex);
   cudaFree(m->coeff_tmp);
+  m->ws_fshared.release();
   m->ws_ex.release();
   m->ws_params.release();
   m->ws_disp.release();
@@ -142,6 +144,11 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
     m->tri = reinterpret_cast<int4*>(t4);
   }
   VP_TRY(upload(&m->v_int2orig_dev, m->topo.v_int2orig));
+  {
+    std::vector<int> o2i((size_t)ntri);
+    for (int i = 0; i < ntri; ++i) o2i[m->topo.tri_int[4 * (size_t)i + 3]] = i;
+    VP_TRY(upload(&m->t_orig2int_dev, o2i));
+  }
   m->ntiles = (int)m->topo.tiles.size();
   VP_TRY(upload(&m->tiles, m->topo.tiles));
   VP_TRY(upload(&m->ltri, m->topo.ltri));

@@ -2,6 +2,7 @@
 // (utils/cython/mesh_core_cython.pyx:49-78) and the launchers shared with the fused path.
 #include "raster.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -36,11 +37,11 @@ int launch_scatter_generic(int mode, const float* vertices, size_t frame_stride,
   GenericMesh mesh{vertices, triangles, frame_stride};
   dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, nframes);
   if (mode == kModeColors)
-    raster_scatter_kernel<kModeColors, GenericMesh, FullKey><<<grid, kRasterBlock, 0, st>>>(mesh, FullKey(), keys, nullptr,
-                                                                                         ntri, h, w, 0);
+    raster_scatter_kernel<kModeColors, GenericMesh, FullKey><<<grid, kRasterBlock, 0, st>>>(
+        mesh, FullKey(), keys, nullptr, ntri, nframes, 1, h, w, 0);
   else
-    raster_scatter_kernel<kModeTriangles, GenericMesh, FullKey><<<grid, kRasterBlock, 0, st>>>(mesh, FullKey(), keys,
-                                                                                            nullptr, ntri, h, w, 0);
+    raster_scatter_kernel<kModeTriangles, GenericMesh, FullKey><<<grid, kRasterBlock, 0, st>>>(
+        mesh, FullKey(), keys, nullptr, ntri, nframes, 1, h, w, 0);
   VP_LAUNCH_CHECK();
   return VP_OK;
 }
@@ -66,20 +67,23 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
                           int w, cudaStream_t st) {
   if (ntri == 0 || nframes == 0) return VP_OK;
   PackedMesh mesh{vrec, triangles, frame_stride};
-  dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, nframes);
+  static const int fpb_env = [] { const char* e = std::getenv("VPB200_SCATTER_FPB"); return e ? std::atoi(e) : 0; }();
+  const int fpb = fpb_env > 0 ? fpb_env : (nframes >= 16 ? 2 : 1);  // frames per block: indices are loaded once
+  dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, (nframes + fpb - 1) / fpb);
   raster_scatter_kernel<kModeColors, PackedMesh, EpochKey><<<grid, kRasterBlock, 0, st>>>(
-      mesh, make_epoch_key(ntri, epoch), keys, tri_color, ntri, h, w, 1);
+      mesh, make_epoch_key(ntri, epoch), keys, tri_color, ntri, nframes, fpb, h, w, 1);
   VP_LAUNCH_CHECK();
   return VP_OK;
 }
 
-int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, uint32_t epoch,
-                          unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
+int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, const int* t_orig2int,
+                          uint32_t epoch, unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
                           cudaStream_t st) {
   const size_t npix = (size_t)h * w;
   if (nframes == 0 || npix == 0) return VP_OK;
   dim3 grid((unsigned)((npix / 4 + 255) / 256), nframes);
-  resolve_packed_kernel<<<grid, 256, 0, st>>>(keys, make_epoch_key(ntri, epoch), tri_color, image, mask, ntri, npix);
+  resolve_packed_kernel<<<grid, 256, 0, st>>>(keys, make_epoch_key(ntri, epoch), tri_color, t_orig2int, image, mask,
+                                              ntri, npix);
   VP_LAUNCH_CHECK();
   return VP_OK;
 }

@@ -116,78 +116,85 @@ __device__ __forceinline__ void offer_span(const Candidate& c, const KeyMaker& k
 
 // One lane per triangle.  Boxes of up to kSmallBox pixels are walked by the owning lane; larger
 // ones are broadcast through shared memory and walked by the whole warp, one row per iteration.
-// tri_color (may be NULL, kModeColors + PackedMesh only): flat colour per ORIGINAL triangle index,
-// written here so that the resolve pass needs one gather per pixel.
+// tri_color (may be NULL, kModeColors + PackedMesh only): flat colour per triangle, written here so
+// that the resolve pass needs one colour gather per covered pixel.
 // const_init: the initial depth is the constant kInitDepth (infer_bfmvid.py:106), so the strict
 // "d > initial" test (mesh_core.cpp:211) is done here per triangle instead of through init keys.
 template <int MODE, typename Mesh, typename KeyMaker>
 __global__ void __launch_bounds__(kRasterBlock)
-raster_scatter_kernel(Mesh mesh, KeyMaker km, unsigned long long* __restrict__ keys,
-                      uint32_t* __restrict__ tri_color, int ntri, int h, int w, int const_init) {
+raster_scatter_kernel(Mesh mesh, KeyMaker km, unsigned long long* __restrict__ keys_all,
+                      uint32_t* __restrict__ tri_color, int ntri, int nframes, int frames_per_block, int h, int w,
+                      int const_init) {
   __shared__ Candidate s_big[kRasterBlock / 32];
-  const int frame = blockIdx.y;
   const int f = blockIdx.x * kRasterBlock + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
-  keys += (size_t)frame * h * w;
+  int ia = 0, ib = 0, ic = 0;
+  uint32_t id = 0;
+  if (f < ntri) mesh.indices(f, ia, ib, ic, id);  // shared by all the frames this block walks
 
-  Candidate c;
-  c.n = 0;
-  c.id = 0;
-  c.key = 0ull;
-  c.z0 = c.z1 = c.z2 = 0.f;
-  if (f < ntri) {
-    int ia, ib, ic;
-    mesh.indices(f, ia, ib, ic, c.id);
-    float x0, y0, z0, x1, y1, z1, x2, y2, z2;
-    uint32_t r0, r1, r2;
-    mesh.vertex(frame, ia, x0, y0, z0, r0);
-    mesh.vertex(frame, ib, x1, y1, z1, r1);
-    mesh.vertex(frame, ic, x2, y2, z2, r2);
-    if (tri_bbox(c.s, x0, y0, x1, y1, x2, y2, h, w)) {
-      c.n = (c.s.x_hi - c.s.x_lo + 1) * (c.s.y_hi - c.s.y_lo + 1);
-      if (MODE == kModeColors) {
-        const float d = flat_depth(z0, z1, z2);
-        if (!(d == d)) c.n = 0;                          // NaN never wins a '>' test
-        if (const_init && !(d > kInitDepth)) c.n = 0;    // mesh_core.cpp:211 against -99999
-        c.key = km.make(d, c.id);
-        if (tri_color != nullptr && c.n > 0) {
-          // integral colours in [0,255] packed by the vertex kernel: sum <= 765 is exact in float,
-          // so integer arithmetic equals mesh_core.cpp:219
-          const uint32_t r = ((r0 & 255u) + (r1 & 255u) + (r2 & 255u)) / 3u;
-          const uint32_t g = (((r0 >> 8) & 255u) + ((r1 >> 8) & 255u) + ((r2 >> 8) & 255u)) / 3u;
-          const uint32_t b = (((r0 >> 16) & 255u) + ((r1 >> 16) & 255u) + ((r2 >> 16) & 255u)) / 3u;
-          tri_color[(size_t)frame * ntri + c.id] = r | (g << 8) | (b << 16) | 0xFF000000u;
+  const int frame_begin = blockIdx.y * frames_per_block;
+  const int frame_end = min(nframes, frame_begin + frames_per_block);
+  for (int frame = frame_begin; frame < frame_end; ++frame) {
+    unsigned long long* keys = keys_all + (size_t)frame * h * w;
+    Candidate c;
+    c.n = 0;
+    c.id = id;
+    c.key = 0ull;
+    c.z0 = c.z1 = c.z2 = 0.f;
+    if (f < ntri) {
+      float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+      uint32_t r0, r1, r2;
+      mesh.vertex(frame, ia, x0, y0, z0, r0);
+      mesh.vertex(frame, ib, x1, y1, z1, r1);
+      mesh.vertex(frame, ic, x2, y2, z2, r2);
+      if (tri_bbox(c.s, x0, y0, x1, y1, x2, y2, h, w)) {
+        c.n = (c.s.x_hi - c.s.x_lo + 1) * (c.s.y_hi - c.s.y_lo + 1);
+        if (MODE == kModeColors) {
+          const float d = flat_depth(z0, z1, z2);
+          if (!(d == d)) c.n = 0;                          // NaN never wins a '>' test
+          if (const_init && !(d > kInitDepth)) c.n = 0;    // mesh_core.cpp:211 against -99999
+          c.key = km.make(d, c.id);
+        } else {
+          c.z0 = z0;
+          c.z1 = z1;
+          c.z2 = z2;
         }
-      } else {
-        c.z0 = z0;
-        c.z1 = z1;
-        c.z2 = z2;
+        if (c.n > 0) tri_edges(c.s, x0, y0, x1, y1, x2, y2);
       }
-      if (c.n > 0) tri_edges(c.s, x0, y0, x1, y1, x2, y2);
+      if (MODE == kModeColors && tri_color != nullptr) {
+        // integral colours in [0,255] packed by the vertex kernel: sum <= 765 is exact in float, so
+        // integer arithmetic equals mesh_core.cpp:219.  Indexed by the INTERNAL triangle number:
+        // a coalesced store; the resolve pass maps the winner's original index back.
+        const uint32_t r = ((r0 & 255u) + (r1 & 255u) + (r2 & 255u)) / 3u;
+        const uint32_t g = (((r0 >> 8) & 255u) + ((r1 >> 8) & 255u) + ((r2 >> 8) & 255u)) / 3u;
+        const uint32_t b = (((r0 >> 16) & 255u) + ((r1 >> 16) & 255u) + ((r2 >> 16) & 255u)) / 3u;
+        tri_color[(size_t)frame * ntri + f] = r | (g << 8) | (b << 16) | 0xFF000000u;
+      }
     }
-  }
 
-  if (c.n > 0 && c.n <= kSmallBox) {
-    for (int y = c.s.y_lo; y <= c.s.y_hi; ++y) offer_span<MODE>(c, km, y, c.s.x_lo, c.s.x_hi, 1, keys, h, w);
-  }
-  unsigned big = __ballot_sync(0xFFFFFFFFu, c.n > kSmallBox);
-  Candidate* slot = &s_big[threadIdx.x >> 5];
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    __syncwarp();
-    if ((int)lane == src) *slot = c;
-    __syncwarp();
-    const Candidate o = *slot;
-    const int bw = o.s.x_hi - o.s.x_lo + 1;
-    if (bw >= 16) {  // wide box: the warp strides along x, row by row
-      for (int y = o.s.y_lo; y <= o.s.y_hi; ++y) offer_span<MODE>(o, km, y, o.s.x_lo + (int)lane, o.s.x_hi, 32, keys, h, w);
-    } else {         // narrow box: 32 / bw' rows at a time (bw' = bw rounded up to a power of two)
-      const int bwp = bw <= 1 ? 1 : (bw <= 2 ? 2 : (bw <= 4 ? 4 : (bw <= 8 ? 8 : 16)));
-      const int rows_per_iter = 32 / bwp;
-      const int dx = (int)lane & (bwp - 1), dy = (int)lane / bwp;
-      for (int y = o.s.y_lo + dy; y <= o.s.y_hi; y += rows_per_iter)
-        if (dx < bw) offer_span<MODE>(o, km, y, o.s.x_lo + dx, o.s.x_lo + dx, 1, keys, h, w);
+    if (c.n > 0 && c.n <= kSmallBox) {
+      for (int y = c.s.y_lo; y <= c.s.y_hi; ++y) offer_span<MODE>(c, km, y, c.s.x_lo, c.s.x_hi, 1, keys, h, w);
+    }
+    unsigned big = __ballot_sync(0xFFFFFFFFu, c.n > kSmallBox);
+    Candidate* slot = &s_big[threadIdx.x >> 5];
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      __syncwarp();
+      if ((int)lane == src) *slot = c;
+      __syncwarp();
+      const Candidate o = *slot;
+      const int bw = o.s.x_hi - o.s.x_lo + 1;
+      if (bw >= 16) {  // wide box: the warp strides along x, row by row
+        for (int y = o.s.y_lo; y <= o.s.y_hi; ++y)
+          offer_span<MODE>(o, km, y, o.s.x_lo + (int)lane, o.s.x_hi, 32, keys, h, w);
+      } else {         // narrow box: 32 / bw' rows at a time (bw' = bw rounded up to a power of two)
+        const int bwp = bw <= 1 ? 1 : (bw <= 2 ? 2 : (bw <= 4 ? 4 : (bw <= 8 ? 8 : 16)));
+        const int rows_per_iter = 32 / bwp;
+        const int dx = (int)lane & (bwp - 1), dy = (int)lane / bwp;
+        for (int y = o.s.y_lo + dy; y <= o.s.y_hi; y += rows_per_iter)
+          if (dx < bw) offer_span<MODE>(o, km, y, o.s.x_lo + dx, o.s.x_lo + dx, 1, keys, h, w);
+      }
     }
   }
 }
@@ -257,7 +264,8 @@ __global__ void resolve_triangles_kernel(const unsigned long long* __restrict__ 
 // Requires (h*w) % 4 == 0.
 __global__ void __launch_bounds__(256)
 resolve_packed_kernel(const unsigned long long* __restrict__ keys, EpochKey km,
-                      const uint32_t* __restrict__ tri_color, unsigned char* __restrict__ image,
+                      const uint32_t* __restrict__ tri_color, const int* __restrict__ t_orig2int,
+                      unsigned char* __restrict__ image,
                       unsigned char* __restrict__ mask, int ntri, size_t npix) {
   const int frame = blockIdx.y;
   const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
@@ -271,8 +279,8 @@ resolve_packed_kernel(const unsigned long long* __restrict__ keys, EpochKey km,
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const bool live = k[i] >= km.epoch_field;  // written during this chunk
-    const uint32_t t = km.tri_mask - (static_cast<uint32_t>(k[i]) & km.tri_mask);
-    col[i] = live ? __ldg(tc + t) : 0u;
+    const uint32_t t = km.tri_mask - (static_cast<uint32_t>(k[i]) & km.tri_mask);  // winner's ORIGINAL index
+    col[i] = live ? __ldg(tc + __ldg(t_orig2int + t)) : 0u;
   }
   // 12 bytes of RGB for 4 pixels as three 32-bit words
   const uint32_t w0 = (col[0] & 0xFFFFFFu) | ((col[1] & 0xFFu) << 24);

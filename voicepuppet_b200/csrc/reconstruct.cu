@@ -5,6 +5,7 @@
 // :35-52 (Compute_norm), :100-120 (Projection_layer), :129-168 (Illumination_layer),
 // :172-223 (Reconstruction / Reconstruction_rotation).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "launch.h"
@@ -164,6 +165,12 @@ int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
 //      raster record (x, S - y, -z, rgb bytes) and/or the reference's per-vertex outputs.
 // Shared memory is double buffered across frames, so a frame costs two block barriers.
 // =========================================================================================
+struct FrameShared {   // per-frame constants staged in shared memory
+  FrameParams par;     // 192 B: rotation (float64), translation, gamma
+  float rot[12];       // rotation as float32
+  float sh[28];        // gamma with the SH band constants (and the 0.8 ambient) folded in: [3][9]
+};
+
 struct VertexArgs {
   const TileDesc* tiles;
   const uint32_t* ltri;
@@ -174,7 +181,7 @@ struct VertexArgs {
   const float* tex;
   const float* disp;
   size_t disp_stride;
-  const FrameParams* params;
+  const FrameShared* fshared;  // per-frame constants prepared by frame_prep_kernel
   int nframes;
   int frames_per_block;
   int rotate_first;
@@ -186,11 +193,35 @@ struct VertexArgs {
   int nver;
 };
 
-struct FrameShared {   // per-frame constants staged in shared memory
-  FrameParams par;     // 192 B: rotation (float64), translation, gamma
-  float rot[12];       // rotation as float32
-  float sh[28];        // gamma with the SH band constants (and the 0.8 ambient) folded in: [3][9]
-};
+
+static_assert(sizeof(FrameShared) == 352, "FrameShared layout");
+
+// Per-frame constants, once per frame instead of once per (tile, frame): the rotation as float32 and
+// the SH coefficients with the band constants folded in (Illumination_layer, reconstruct_mesh.py:133-153:
+// Y_k = K_k * b_k(n), lit_c = sum_k Y_k gamma'_ck with gamma' = gamma + 0.8 on band 0; K_k are products
+// of a0..a2 and c0..c2 evaluated in float64).
+__global__ void frame_prep_kernel(const FrameParams* __restrict__ params, FrameShared* __restrict__ out, int nframes) {
+  const int f = blockIdx.x * (blockDim.x / 64) + threadIdx.x / 64;
+  const int t = threadIdx.x % 64;
+  if (f >= nframes) return;
+  const FrameParams& p = params[f];
+  FrameShared& o = out[f];
+  if (t < 48) reinterpret_cast<uint32_t*>(&o.par)[t] = reinterpret_cast<const uint32_t*>(&p)[t];
+  if (t < 12) o.rot[t] = t < 9 ? (float)p.rot[t] : 0.f;
+  if (t >= 32 && t < 60) {
+    const int i = t - 32;
+    if (i >= 27) {
+      o.sh[i] = 0.f;
+    } else {
+      const int k = i % 9;
+      const float kk = (k == 0) ? 0.8862269254527579f
+                                : (k <= 3 ? 1.772453850905516f
+                                          : (k == 6 ? 0.7006239020497412f : (k == 8 ? 1.2135161953473121f : 2.4270323906946243f)));
+      const float sign = (k == 1 || k == 3 || k == 5 || k == 7) ? -1.f : 1.f;
+      o.sh[i] = sign * kk * (p.gamma[i] + (k == 0 ? 0.8f : 0.f));
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs a) {
   __shared__ float4 s_pos[2][kTileLV];
@@ -271,21 +302,8 @@ __global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs
     const int buf = (f - f_begin) & 1;
     FrameShared& fs = s_frame[buf];
     // ---- phase 1: per-frame constants and local positions -> shared memory ----------------
-    if (tid < 48) {
-      reinterpret_cast<uint32_t*>(&fs.par)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.params + f) + tid);
-    } else if (tid < 57) {
-      fs.rot[tid - 48] = (float)__ldg(a.params[f].rot + (tid - 48));
-    } else if (tid >= 64 && tid < 91) {
-      // Illumination_layer (reconstruct_mesh.py:133-153): Y_k = K_k * b_k(n), lit_c = sum_k Y_k gamma'_ck with
-      // gamma' = gamma + 0.8 on band 0; K_k (products of a0..a2, c0..c2, evaluated in float64) folded in here
-      const int k = (tid - 64) % 9;
-      const float kk = (k == 0) ? 0.8862269254527579f
-                                : (k <= 3 ? 1.772453850905516f
-                                          : (k == 6 ? 0.7006239020497412f : (k == 8 ? 1.2135161953473121f : 2.4270323906946243f)));
-      const float sign = (k == 1 || k == 3 || k == 5 || k == 7) ? -1.f : 1.f;
-      const float g = __ldg(a.params[f].gamma + (tid - 64)) + (k == 0 ? 0.8f : 0.f);
-      fs.sh[tid - 64] = sign * kk * g;
-    }
+    if (tid < (int)(sizeof(FrameShared) / 4))
+      reinterpret_cast<uint32_t*>(&fs)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.fshared + f) + tid);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
       if (q < nq_v) s_pos[buf][tid + q * kTileV] = make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
@@ -409,9 +427,14 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.tex = m->have_tex ? m->tex : nullptr;
   a.disp = disp_dev;
   a.disp_stride = (size_t)m->rows_pad;
-  a.params = params_dev;
+  VP_CUDA(m->ws_fshared.reserve((size_t)nframes * sizeof(FrameShared), m->device));
+  FrameShared* fshared = m->ws_fshared.as<FrameShared>();
+  frame_prep_kernel<<<(nframes + 3) / 4, 256, 0, st>>>(params_dev, fshared, nframes);
+  VP_LAUNCH_CHECK();
+  a.fshared = fshared;
   a.nframes = nframes;
-  a.frames_per_block = nframes >= 16 ? 4 : 1;
+  static const int fpb_env = [] { const char* e = std::getenv("VPB200_VERTEX_FPB"); return e ? std::atoi(e) : 0; }();
+  a.frames_per_block = fpb_env > 0 ? fpb_env : (nframes >= 16 ? 4 : 1);
   a.rotate_first = rotate_first;
   a.has_out = (out.shape || out.norm || out.color || out.proj || out.zbuf) ? 1 : 0;
   a.focal = focal;

@@ -20,18 +20,21 @@ size_t env_size(const char* name, size_t dflt) {
   return v > 0 ? (size_t)v : dflt;
 }
 
-// Frames per raster chunk: the chunk's vertex records, z-buffer keys and per-triangle colours
-// (plus its slice of the displacements) should stay L2 resident (VPB200_CHUNK_MB, default 64 MB);
-// the sequence is then cut into equal chunks so that no launch runs nearly empty.
-int chunk_frames(const vp_model* m, int res, int nframes) {
-  const size_t per_frame = (size_t)m->rows_pad * 4 + (size_t)m->vrec_stride * 16 + (size_t)res * res * 8 +
-                           (size_t)m->ntri * 4;
+// Frames per raster chunk.  Measured on B200 (profiles/r01_chunk_sweep.txt): large launches beat
+// L2 residency of the intermediates -- one 75-frame chunk at 256x256 (134 MB of intermediates) runs 10 %
+// faster than two 38-frame chunks -- so the device-output path takes the largest chunk within
+// VPB200_CHUNK_MB (default 192 MB of vertex records + z-buffer keys + per-triangle colours).  The
+// host-output path cuts the sequence into at least four chunks so that the device->host drain of one
+// chunk overlaps the rendering of the next.  Chunks are equal-sized so that no launch runs nearly empty.
+int chunk_frames(const vp_model* m, int res, int nframes, bool host_outputs) {
+  const size_t per_frame = (size_t)m->vrec_stride * 16 + (size_t)res * res * 8 + (size_t)m->ntri * 4;
   const size_t forced = env_size("VPB200_CHUNK_FRAMES", 0);
-  size_t c = forced ? forced : (env_size("VPB200_CHUNK_MB", 64) << 20) / per_frame;
+  size_t c = forced ? forced : (env_size("VPB200_CHUNK_MB", 192) << 20) / per_frame;
   c = std::max<size_t>(c, 4);
   c = std::min<size_t>(c, 1024);
   const size_t t = (size_t)std::max(nframes, 1);
   if (forced) return (int)std::min(c, t);
+  if (host_outputs) c = std::min(c, std::max<size_t>(8, (t + 3) / 4));
   const size_t nchunks = std::max<size_t>(1, (t * 10 + c * 11 - 1) / (c * 11));  // ceil(t / (1.1 c))
   return (int)((t + nchunks - 1) / nchunks);
 }
@@ -111,7 +114,7 @@ int render_chunk(vp_model* m, int n, const float* disp_dev, const FrameParams* p
   VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, epoch, n, m->ntri, res, res, st));
   prof.end();
   prof.begin(kProfResolve);
-  VP_TRY(launch_resolve_packed(keys, tricol, epoch, image_dev, mask_dev, n, m->ntri, res, res, st));
+  VP_TRY(launch_resolve_packed(keys, tricol, m->t_orig2int_dev, epoch, image_dev, mask_dev, n, m->ntri, res, res, st));
   prof.end();
   return VP_OK;
 }
@@ -149,7 +152,7 @@ extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_
   VP_REQUIRE(m->have_base && m->have_tex, "no identity set (call vp_set_identity first)");
   VP_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int chunk = chunk_frames(m, res, nframes);
+  const int chunk = chunk_frames(m, res, nframes, false);
   const int group = basis_group_frames(chunk, nframes);
   VP_TRY(reserve_chunk(m, chunk, group, res));
   const size_t npix = (size_t)res * res;
@@ -198,7 +201,7 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
   const float* ex_dev = fr->ex ? m->ws_ex.as<float>() : nullptr;
   const FrameParams* params_dev = m->ws_params.as<FrameParams>();
 
-  const int chunk = chunk_frames(m, res, T);
+  const int chunk = chunk_frames(m, res, T, outputs_on_device == 0);
   const int group = basis_group_frames(chunk, T);
   VP_TRY(reserve_chunk(m, chunk, group, res));
   const size_t npix = (size_t)res * res;

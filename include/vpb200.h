@@ -187,7 +187,8 @@ int vp_projection(int device, int n, const double* shape, const double* rotation
  * reconstruction, colours clipped to [0,255] and truncated, vertices (x, S - y, -z) scaled by
  * res/224, flat-shaded z-buffer rasterization at h = w = res.
  *   image[nframes][res][res][3] u8, face_mask[nframes][res][res] u8 (NULL ok).
- * outputs_on_device: 0 = host pointers (copied back, pipelined per chunk), 1 = device pointers. */
+ * outputs_on_device: 0 = host pointers (copied back, pipelined per chunk; synchronous),
+ *                    1 = device pointers (asynchronous: ordered on `stream`, nothing is synchronised). */
 int vp_render_sequence(vp_model* m, const vp_frames* frames, int res, unsigned char* image,
                        unsigned char* face_mask, int outputs_on_device, void* stream);
 

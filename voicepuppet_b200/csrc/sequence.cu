@@ -216,13 +216,7 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
                         params_dev + t0, fr->rotate_shape_first, res, image + (size_t)t0 * npix * 3,
                         face_mask ? face_mask + (size_t)t0 * npix : nullptr, st, prof);
     }
-    if (rc == VP_OK) {
-      cudaError_t e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) {
-        set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
-        rc = VP_ERR_CUDA;
-      }
-    }
+    // device outputs: asynchronous, ordered on `stream` like any other work the caller enqueues there
   } else {
     // double-buffered: chunk i renders while chunk i-1 drains to the host on the copy stream
     for (int b = 0; b < 2; ++b) {

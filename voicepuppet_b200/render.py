@@ -102,10 +102,53 @@ def shard_bounds(n_frames, world_size, rank):
   return begin, min(begin + per, n_frames)
 
 
-def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=None, render_fn=None):
+def gather_groups(n_local, n_groups=None):
+  """Cut a rank's frames into groups whose NCCL gather overlaps the rendering of the next group."""
+  if n_groups is None:
+    n_groups = 1 if n_local < 32 else min(4, n_local // 16)
+  n_groups = max(1, min(n_groups, max(n_local, 1)))
+  edges = [round(i * n_local / n_groups) for i in range(n_groups + 1)]
+  return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+
+def pipelined_gather(render_group, local, per, world, rank, group=None, n_groups=None):
+  """Render `local` ([per,res,res,3] uint8 on this rank's GPU) group by group with
+  ``render_group(a, b)`` (asynchronous on the current stream) and gather every finished group to
+  rank 0 on a side stream, so that the transfer of group g runs under the rendering of group g+1.
+  Returns the [world*per,res,res,3] tensor on rank 0 (frames ordered by rank), None elsewhere."""
+  import torch
+  import torch.distributed as dist
+  full = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if rank == 0 else None
+  compute = torch.cuda.current_stream(local.device)
+  comm = _comm_stream(local.device)
+  for a, b in gather_groups(per, n_groups):
+    render_group(a, b)
+    done = torch.cuda.Event()
+    done.record(compute)
+    comm.wait_event(done)
+    with torch.cuda.stream(comm):
+      dst = [full[r * per + a:r * per + b] for r in range(world)] if rank == 0 else None
+      dist.gather(local[a:b], dst, dst=0, group=group)
+  compute.wait_stream(comm)
+  return full
+
+
+_comm_streams = {}
+
+
+def _comm_stream(device):
+  import torch
+  key = (device.type, device.index)
+  if key not in _comm_streams:
+    _comm_streams[key] = torch.cuda.Stream(device=device)
+  return _comm_streams[key]
+
+
+def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=None, render_fn=None, n_groups=None):
   """Frames are independent, so rank r renders frames [r*ceil(T/W), (r+1)*ceil(T/W)) on its own GPU
   with no communication; the only collective is the gather of the uint8 frames to rank 0 (NCCL
-  over NVLink when the group's backend is nccl; gloo in the CPU tests, which also substitute
+  over NVLink when the group's backend is nccl, issued per group of frames on a side stream so that
+  it overlaps the rendering of the next group; gloo in the CPU tests, which also substitute
   ``render_fn``).  Returns [T,res,res,3] uint8 on rank 0 (a torch tensor on the group's device)
   and None elsewhere.  The jitter sequence is a function of the global frame index, so every rank
   generates all of it and slices its shard."""
@@ -124,16 +167,21 @@ def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=N
   use_cuda = dist.get_backend(group) == 'nccl'
   device = torch.device('cuda', torch.cuda.current_device()) if use_cuda else torch.device('cpu')
   local = torch.zeros((per, res, res, 3), dtype=torch.uint8, device=device)
+  shard_angles = None if angles is None else np.asarray(angles)[begin:end]
+  if use_cuda and render_fn is None:
+    def render_group(a, b):
+      b = min(b, end - begin)
+      if b > a:
+        render_sequence(coeffs[begin + a:begin + b], facemodel, res=res,
+                        angles=None if shard_angles is None else shard_angles[a:b], device=device.index,
+                        out=local[a:b])
+    full = pipelined_gather(render_group, local, per, world, rank, group, n_groups)
+    return None if rank != 0 else full[:t]
+  if render_fn is None:
+    raise RuntimeError('render_sequence_sharded needs CUDA ranks (nccl backend); there is no CPU path')
   if end > begin:
-    shard_angles = None if angles is None else np.asarray(angles)[begin:end]
-    if render_fn is not None:
-      frames = render_fn(coeffs[begin:end], facemodel, res=res, angles=shard_angles)
-      local[:end - begin].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
-    elif use_cuda:
-      render_sequence(coeffs[begin:end], facemodel, res=res, angles=shard_angles, device=device.index,
-                      out=local[:end - begin])
-    else:
-      raise RuntimeError('render_sequence_sharded needs CUDA ranks (nccl backend); there is no CPU path')
+    frames = render_fn(coeffs[begin:end], facemodel, res=res, angles=shard_angles)
+    local[:end - begin].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
   gathered = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
   dist.gather(local, gathered, dst=0, group=group)
   if rank != 0:

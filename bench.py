@@ -198,29 +198,25 @@ def run_ours(args):
   dm.set_identity(coeffs[0:1, :80], coeffs[0:1, 144:224])
 
   # device-resident inputs
-  params = np.zeros(t_local, dtype=_lib.FRAME_PARAMS_DTYPE)
-  params['rotation'] = rotation_matrices(angles).reshape(t_local, 9)
-  params['translation'] = coeffs[:, 254:257]
-  params['gamma'] = coeffs[:, 227:254]
-  ex_dev = torch.from_numpy(np.ascontiguousarray(coeffs[:, 80:144])).to(dev)
-  params_dev = torch.from_numpy(params.view(np.uint8).reshape(t_local, 192)).to(dev)
+  ex_dev, params_dev = render.device_inputs(coeffs, angles, dev)
   frames_dev = torch.empty((t_local, res, res, 3), dtype=torch.uint8, device=dev)
   mask_dev = torch.empty((t_local, res, res), dtype=torch.uint8, device=dev)
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
   lib = _lib.lib()
   npix = res * res
 
-  def render_group(a, b):
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(lib.vp_render_sequence_dev(dm.handle, b - a, ex_dev.data_ptr() + a * 256, params_dev.data_ptr() + a * 192,
-                                          1, res, frames_dev.data_ptr() + a * npix * 3, mask_dev.data_ptr() + a * npix,
-                                          stream))
+  gather_mode = os.environ.get('VPB200_GATHER', 'p2p')
+  peer = None
+  if world > 1 and gather_mode == 'p2p':
+    peer = render.PeerFrameBuffer(t_local, res, world, rank, dev)
 
   def step():
     if world == 1:
-      render_group(0, t_local)
-    else:   # groups of frames: the NCCL gather of one group runs under the rendering of the next
-      render.pipelined_gather(render_group, frames_dev, t_local, world, rank)
+      render.render_device(dm, ex_dev, params_dev, True, res, frames_dev, mask_dev)
+    elif peer is not None:   # every rank's resolve kernel stores straight into rank 0's buffer over NVLink
+      peer.render_into(dm, ex_dev, params_dev, True)
+    else:                    # baseline: render locally, NCCL gather to rank 0
+      render.pipelined_gather(dm, ex_dev, params_dev, True, res, frames_dev, world, rank)
 
   def barrier():
     if world > 1:
@@ -240,9 +236,9 @@ def run_ours(args):
   ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
   barrier()
   for i in range(args.steps):
-    flush.zero_()                      # L2 flush between timed steps (outside the per-step events)
     if world > 1:
       dist.barrier()
+    flush.zero_()                      # L2 flush between timed steps (outside the per-step events)
     starts[i].record()
     step()
     ends[i].record()
@@ -328,7 +324,7 @@ def run_ours(args):
                    'frames_per_gpu': t_local, 'resolution': res,
                    'model': 'synthetic BFM-shaped model, 35709 vertices / 70789 triangles, seed 0', 'coeff_seed': 1,
                    'l2': 'flushed between timed steps (256 MiB write)',
-                   'gather': 'NCCL gather of uint8 frames to rank 0 inside the step, per group of frames on a side stream' if world > 1 else 'none'},
+                   'gather': ('none' if world == 1 else ('frames stored straight into rank 0 buffer over NVLink (CUDA IPC peer memory) by the resolve kernel, device-side completion flags' if peer is not None else 'NCCL gather of uint8 frames to rank 0 inside the step'))},
         'roofline': roofline,
         'roofline_pipeline': {'algorithmic_bytes': total_bytes, 'achieved': round(pipeline_gbs, 1), 'peak': peak,
                               'unit': 'GB/s', 'frac': round(pipeline_gbs / peak, 4)},

@@ -61,6 +61,21 @@ int vp_device_count(void);
 int vp_host_alloc(void** out, size_t bytes);
 int vp_host_free(void* p);
 
+/* Peer memory (CUDA IPC over NVLink), for the multi-GPU gather without a copy: rank 0 exports the
+ * buffer that receives every rank's frames, the other ranks open it and pass `base + offset + their
+ * slice` as image_dev to vp_render_sequence_dev: the resolve kernel's stores land in rank 0's HBM.
+ *   vp_ipc_export: handle64 = cudaIpcMemHandle_t of the allocation containing dev_ptr, *offset = dev_ptr - base
+ *   vp_ipc_open:   maps the allocation into this process on `device` (peer access enabled lazily) */
+int vp_ipc_export(const void* dev_ptr, unsigned char* handle64, unsigned long long* offset);
+int vp_ipc_open(const unsigned char* handle64, int device, void** base_out);
+int vp_ipc_close(void* base);
+/* Completion flags in (peer-mapped) device memory: vp_peer_signal publishes `value` in *flag_dev with
+ * system-scope release semantics after everything enqueued on `stream` before it; vp_peer_wait makes
+ * `stream` wait until flags_dev[0..n) have all reached `value` (n <= 32; wrap-around safe compare;
+ * traps after a bounded spin instead of hanging).  Use an increasing step counter as `value`. */
+int vp_peer_signal(unsigned int* flag_dev, unsigned int value, void* stream);
+int vp_peer_wait(const unsigned int* flags_dev, int n, unsigned int value, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * mesh_core_cython replacements: caller-initialised buffers, mutated in place.
  * --------------------------------------------------------------------------------------- */
@@ -204,6 +219,15 @@ typedef struct vp_frame_params {
 int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev,
                            const vp_frame_params* params_dev, int rotate_shape_first, int res,
                            unsigned char* image_dev, unsigned char* face_mask_dev, void* stream);
+
+/* vp_render_sequence_dev in chunks of `notify_frames` frames, recording events[i] (cudaEvent_t handles
+ * owned by the caller) on `stream` as soon as chunk i is complete, so that finished frames can be moved
+ * (NCCL gather to rank 0, device->host copy) while the rest is still rendering.  The expression
+ * contraction still runs once for the whole call.  nevents >= ceil(nframes / notify_frames). */
+int vp_render_sequence_dev_notify(vp_model* m, int nframes, const float* ex_dev,
+                                  const vp_frame_params* params_dev, int rotate_shape_first, int res,
+                                  unsigned char* image_dev, unsigned char* face_mask_dev, void* stream,
+                                  int notify_frames, void** events, int nevents);
 
 /* The expression contraction alone (device pointers, asynchronous on `stream`):
  * disp_dev[t][r] = sum_k exBase[r][k] * ex_dev[t][k], r in the library's internal row order

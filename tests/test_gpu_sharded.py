@@ -20,7 +20,7 @@ def _free_port():
   return port
 
 
-def _worker(rank, world, port, n_frames, res, queue):
+def _worker(rank, world, port, n_frames, res, queue, gather):
   sys.path.insert(0, ROOT)
   import torch
   import torch.distributed as dist
@@ -32,7 +32,7 @@ def _worker(rank, world, port, n_frames, res, queue):
   try:
     model = synthetic.cached_model()
     coeffs = synthetic.make_coeffs(n_frames, seed=9)
-    out = render.render_sequence_sharded(coeffs, model, res=res, angles='jitter', n_groups=3)
+    out = render.render_sequence_sharded(coeffs, model, res=res, angles='jitter', notify_frames=13, gather=gather)
     torch.cuda.synchronize()
     if rank == 0:
       queue.put(out.cpu().numpy())
@@ -42,7 +42,8 @@ def _worker(rank, world, port, n_frames, res, queue):
     dist.destroy_process_group()
 
 
-def test_two_gpu_shards_equal_single_gpu():
+@pytest.mark.parametrize('gather', ['p2p', 'nccl'])
+def test_two_gpu_shards_equal_single_gpu(gather):
   import torch
   if torch.cuda.device_count() < 2:
     pytest.skip('needs 2 GPUs')
@@ -53,7 +54,7 @@ def test_two_gpu_shards_equal_single_gpu():
   ctx = mp.get_context('spawn')
   queue = ctx.Queue()
   port = _free_port()
-  procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, res, queue)) for r in range(world)]
+  procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, res, queue, gather)) for r in range(world)]
   for p in procs:
     p.start()
   got = queue.get(timeout=240)

@@ -57,6 +57,11 @@ SIGNATURES = {
     'vp_device_count': (_i, []),
     'vp_host_alloc': (_i, [ctypes.POINTER(_vp), _sz]),
     'vp_host_free': (_i, [_vp]),
+    'vp_ipc_export': (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_ulonglong)]),
+    'vp_ipc_open': (_i, [_vp, _i, ctypes.POINTER(_vp)]),
+    'vp_ipc_close': (_i, [_vp]),
+    'vp_peer_signal': (_i, [_vp, ctypes.c_uint, _vp]),
+    'vp_peer_wait': (_i, [_vp, _i, ctypes.c_uint, _vp]),
     'vp_render_colors_core': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
     'vp_rasterize_triangles_core': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     'vp_render_colors_batch_dev': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -80,6 +85,7 @@ SIGNATURES = {
     'vp_projection': (_i, [_i, _i, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp, _vp]),
     'vp_render_sequence': (_i, [_vp, ctypes.POINTER(VpFrames), _i, _vp, _vp, _i, _vp]),
     'vp_render_sequence_dev': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    'vp_render_sequence_dev_notify': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i]),
     'vp_basis_dev': (_i, [_vp, _vp, _vp, _i, _vp]),
     'vp_model_rows_pad': (_i, [_vp]),
     'vp_debug_basis_trace': (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -2,6 +2,7 @@
 #include "common.h"
 
 #include <cstring>
+#include <cstdint>
 
 namespace vp {
 
@@ -47,5 +48,57 @@ extern "C" int vp_host_alloc(void** out, size_t bytes) {
 
 extern "C" int vp_host_free(void* p) {
   if (p) VP_CUDA(cudaFreeHost(p));
+  return VP_OK;
+}
+
+// ---- peer memory (CUDA IPC): lets every rank's resolve kernel store its frames straight into rank 0's
+// buffer over NVLink, so the gather needs no separate copy --------------------------------------------
+#include <cuda.h>
+
+namespace {
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+GetAddressRangeFn address_range_fn() {
+  static GetAddressRangeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<GetAddressRangeFn>(p);
+  }();
+  return fn;
+}
+}  // namespace
+
+extern "C" int vp_ipc_export(const void* dev_ptr, unsigned char* handle64, unsigned long long* offset) {
+  VP_REQUIRE(dev_ptr && handle64 && offset, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  GetAddressRangeFn range = address_range_fn();
+  VP_REQUIRE(range != nullptr, "cuMemGetAddressRange unavailable");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range(&base, &size, (CUdeviceptr)(uintptr_t)dev_ptr) != CUDA_SUCCESS) {
+    vp::set_error("cuMemGetAddressRange failed for %p", dev_ptr);
+    return VP_ERR_CUDA;
+  }
+  cudaIpcMemHandle_t h;
+  VP_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+  std::memcpy(handle64, &h, 64);
+  *offset = (unsigned long long)((uintptr_t)dev_ptr - (uintptr_t)base);
+  return VP_OK;
+}
+
+extern "C" int vp_ipc_open(const unsigned char* handle64, int device, void** base_out) {
+  VP_REQUIRE(handle64 && base_out, "null argument");
+  VP_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  VP_CUDA(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return VP_OK;
+}
+
+extern "C" int vp_ipc_close(void* base) {
+  if (base) VP_CUDA(cudaIpcCloseMemHandle(base));
   return VP_OK;
 }

@@ -142,23 +142,27 @@ int check_sequence_args(const vp_model* m, int nframes, int res, const void* ima
 
 using namespace vp;
 
-extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev, const vp_frame_params* params_dev,
-                                      int rotate_shape_first, int res, unsigned char* image_dev,
-                                      unsigned char* face_mask_dev, void* stream) {
+static int render_sequence_dev_impl(vp_model* m, int nframes, const float* ex_dev, const vp_frame_params* params_dev,
+                                    int rotate_shape_first, int res, unsigned char* image_dev,
+                                    unsigned char* face_mask_dev, void* stream, int notify_frames, void** events,
+                                    int nevents) {
   VP_TRY(check_sequence_args(m, nframes, res, image_dev));
   VP_REQUIRE(nframes == 0 || params_dev != nullptr, "null params");
+  VP_REQUIRE(notify_frames >= 0 && (notify_frames == 0 || (events != nullptr && nevents > 0)), "bad notify arguments");
   if (nframes == 0) return VP_OK;
   std::lock_guard<std::mutex> lock(m->mu);
   VP_REQUIRE(m->have_base && m->have_tex, "no identity set (call vp_set_identity first)");
   VP_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int chunk = chunk_frames(m, res, nframes, false);
+  const int chunk = notify_frames > 0 ? notify_frames : chunk_frames(m, res, nframes, false);
+  VP_REQUIRE(notify_frames == 0 || (nframes + chunk - 1) / chunk <= nevents, "not enough events for the chunks");
   const int group = basis_group_frames(chunk, nframes);
   VP_TRY(reserve_chunk(m, chunk, group, res));
   const size_t npix = (size_t)res * res;
   Profiler prof(m, st);
   int rc = VP_OK;
-  for (int t0 = 0; t0 < nframes && rc == VP_OK; t0 += chunk) {
+  int ci = 0;
+  for (int t0 = 0; t0 < nframes && rc == VP_OK; t0 += chunk, ++ci) {
     const int n = std::min(chunk, nframes - t0);
     if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, nframes, group, st, prof);
     if (rc != VP_OK) break;
@@ -166,10 +170,30 @@ extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_
                       reinterpret_cast<const FrameParams*>(params_dev) + t0, rotate_shape_first, res,
                       image_dev + (size_t)t0 * npix * 3, face_mask_dev ? face_mask_dev + (size_t)t0 * npix : nullptr,
                       st, prof);
+    if (rc == VP_OK && notify_frames > 0) VP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(events[ci]), st));
   }
   if (rc != VP_OK) m->key_epoch = 0;
   prof.finish();
   return rc;
+}
+
+extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev, const vp_frame_params* params_dev,
+                                      int rotate_shape_first, int res, unsigned char* image_dev,
+                                      unsigned char* face_mask_dev, void* stream) {
+  return render_sequence_dev_impl(m, nframes, ex_dev, params_dev, rotate_shape_first, res, image_dev, face_mask_dev,
+                                  stream, 0, nullptr, 0);
+}
+
+// Same, rendered in chunks of `notify_frames` frames with events[i] (cudaEvent_t) recorded on `stream`
+// as soon as chunk i is complete: lets the caller start moving finished frames (NCCL gather, D2H copy)
+// while the rest of the sequence is still rendering.  The basis contraction still runs once per group.
+extern "C" int vp_render_sequence_dev_notify(vp_model* m, int nframes, const float* ex_dev,
+                                             const vp_frame_params* params_dev, int rotate_shape_first, int res,
+                                             unsigned char* image_dev, unsigned char* face_mask_dev, void* stream,
+                                             int notify_frames, void** events, int nevents) {
+  VP_REQUIRE(notify_frames > 0, "notify_frames must be positive");
+  return render_sequence_dev_impl(m, nframes, ex_dev, params_dev, rotate_shape_first, res, image_dev, face_mask_dev,
+                                  stream, notify_frames, events, nevents);
 }
 
 extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, unsigned char* image,

@@ -102,35 +102,155 @@ def shard_bounds(n_frames, world_size, rank):
   return begin, min(begin + per, n_frames)
 
 
-def gather_groups(n_local, n_groups=None):
-  """Cut a rank's frames into groups whose NCCL gather overlaps the rendering of the next group."""
-  if n_groups is None:
-    n_groups = 1 if n_local < 32 else min(4, n_local // 16)
-  n_groups = max(1, min(n_groups, max(n_local, 1)))
-  edges = [round(i * n_local / n_groups) for i in range(n_groups + 1)]
-  return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+def device_inputs(coeffs, angles, device):
+  """Per-frame inputs of the fused path as device tensors: expression coefficients [T,64] float32 and
+  packed vp_frame_params [T,192] uint8 (rotation float64[9] | translation float32[3] | gamma float32[27])."""
+  import torch
+  from . import _lib
+  t = coeffs.shape[0]
+  params = np.zeros(t, dtype=_lib.FRAME_PARAMS_DTYPE)
+  params['rotation'] = rotation_matrices(np.asarray(angles).reshape(t, 3)).reshape(t, 9)
+  params['translation'] = coeffs[:, 254:257]
+  params['gamma'] = coeffs[:, 227:254]
+  ex_dev = torch.from_numpy(np.ascontiguousarray(coeffs[:, 80:144])).to(device)
+  params_dev = torch.from_numpy(params.view(np.uint8).reshape(t, 192)).to(device)
+  return ex_dev, params_dev
 
 
-def pipelined_gather(render_group, local, per, world, rank, group=None, n_groups=None):
-  """Render `local` ([per,res,res,3] uint8 on this rank's GPU) group by group with
-  ``render_group(a, b)`` (asynchronous on the current stream) and gather every finished group to
-  rank 0 on a side stream, so that the transfer of group g runs under the rendering of group g+1.
-  Returns the [world*per,res,res,3] tensor on rank 0 (frames ordered by rank), None elsewhere."""
+def render_device(dm, ex_dev, params_dev, rotate_first, res, out, mask=None, notify_frames=0):
+  """vp_render_sequence_dev(_notify) on torch CUDA tensors, asynchronous on the current stream.
+  With notify_frames > 0 returns one torch event per chunk of that many frames, recorded when the
+  chunk's frames are complete."""
+  import ctypes
+  import torch
+  from . import _lib
+  t = ex_dev.shape[0]
+  stream = ctypes.c_void_p(torch.cuda.current_stream(ex_dev.device).cuda_stream)
+  mask_ptr = None if mask is None else ctypes.c_void_p(mask.data_ptr())
+  out_ptr = ctypes.c_void_p(out if isinstance(out, int) else out.data_ptr())   # int: a (peer) device address
+  if notify_frames <= 0:
+    _lib.check(_lib.lib().vp_render_sequence_dev(dm.handle, t, ex_dev.data_ptr(), params_dev.data_ptr(),
+                                                 int(bool(rotate_first)), res, out_ptr, mask_ptr, stream))
+    return []
+  n_events = -(-t // notify_frames)
+  events = [torch.cuda.Event() for _ in range(n_events)]
+  for ev in events:
+    ev.record()                      # materialises the underlying cudaEvent_t
+  handles = (ctypes.c_void_p * n_events)(*[ev.cuda_event for ev in events])
+  _lib.check(_lib.lib().vp_render_sequence_dev_notify(dm.handle, t, ex_dev.data_ptr(), params_dev.data_ptr(),
+                                                      int(bool(rotate_first)), res, out_ptr, mask_ptr, stream,
+                                                      notify_frames, handles, n_events))
+  return events
+
+
+def gather_notify_frames(n_local, world):
+  """Frames per notification chunk: the gather of one chunk runs under the rendering of the next.
+  One chunk (no pipelining) for short shards, where smaller launches would cost more than they hide."""
+  if n_local < 256 or world < 2:   # measured: below this the extra launches and NCCL calls cost more than they hide
+    return 0
+  return -(-n_local // 3)
+
+
+def pipelined_gather(dm, ex_dev, params_dev, rotate_first, res, local, world, rank, group=None, notify_frames=None):
+  """Render this rank's frames into `local` ([per,res,res,3] uint8 on its GPU; the trailing frames of a
+  short last shard stay untouched) and gather them to rank 0.  The frames are rendered in chunks and
+  every finished chunk is gathered on a side stream (NCCL over NVLink), so the transfer of chunk c
+  runs under the rendering of chunk c+1.  Returns the [world*per,res,res,3] tensor on rank 0 (frames
+  ordered by rank), None elsewhere."""
   import torch
   import torch.distributed as dist
+  per = local.shape[0]
+  n = ex_dev.shape[0]
   full = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device) if rank == 0 else None
+  if notify_frames is None:
+    notify_frames = gather_notify_frames(per, world)
   compute = torch.cuda.current_stream(local.device)
   comm = _comm_stream(local.device)
-  for a, b in gather_groups(per, n_groups):
-    render_group(a, b)
-    done = torch.cuda.Event()
-    done.record(compute)
-    comm.wait_event(done)
+  if notify_frames <= 0 or notify_frames >= per:
+    if n > 0:
+      render_device(dm, ex_dev, params_dev, rotate_first, res, local)
+    dst = [full[r * per:(r + 1) * per] for r in range(world)] if rank == 0 else None
+    dist.gather(local, dst, dst=0, group=group)
+    return full
+  # every rank walks the same chunk grid over `per` frames, whatever its own frame count
+  events = render_device(dm, ex_dev, params_dev, rotate_first, res, local, notify_frames=notify_frames) if n > 0 else []
+  for c, a in enumerate(range(0, per, notify_frames)):
+    b = min(a + notify_frames, per)
+    if c < len(events):
+      comm.wait_event(events[c])
+    else:
+      comm.wait_stream(compute)
     with torch.cuda.stream(comm):
       dst = [full[r * per + a:r * per + b] for r in range(world)] if rank == 0 else None
       dist.gather(local[a:b], dst, dst=0, group=group)
   compute.wait_stream(comm)
   return full
+
+
+class PeerFrameBuffer(object):
+  """Rank 0's [world*per,res,res,3] uint8 frame buffer mapped into every rank of the node (CUDA IPC over
+  NVLink / NVSwitch).  Each rank's resolve kernel stores its frames straight into its slice of rank 0's
+  HBM, so gathering the frames is fused into the rendering: no copy kernel, no staging buffer; the only
+  collective left is a one-element all-reduce that orders rank 0's consumer after every rank's stores."""
+
+  def __init__(self, per, res, world, rank, device, group=None):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    self.per, self.res, self.world, self.rank, self.group = per, res, world, rank, group
+    self.frame_bytes = res * res * 3
+    self.full = None
+    self._base = None
+    payload = [None]
+    n_bytes = world * per * self.frame_bytes
+    self.device = device
+    self.step = 0
+    if rank == 0:
+      # frames, then one 32-bit completion flag per rank (128-byte aligned)
+      self._storage = torch.zeros(((n_bytes + 127) // 128) * 128 + 128, dtype=torch.uint8, device=device)
+      self.full = self._storage[:n_bytes].view(world * per, res, res, 3)
+      handle = (ctypes.c_ubyte * 64)()
+      offset = ctypes.c_ulonglong()
+      _lib.check(_lib.lib().vp_ipc_export(ctypes.c_void_p(self._storage.data_ptr()), handle, ctypes.byref(offset)))
+      payload = [(bytes(handle), int(offset.value))]
+      torch.cuda.synchronize(device)           # the zeroed flags are in memory before anybody signals
+    dist.broadcast_object_list(payload, src=0, group=group)
+    handle_bytes, offset = payload[0]
+    if rank == 0:
+      start = self._storage.data_ptr()
+    else:
+      base = ctypes.c_void_p()
+      buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle_bytes)
+      _lib.check(_lib.lib().vp_ipc_open(buf, device.index, ctypes.byref(base)))
+      self._base = base
+      start = base.value + offset
+    self.slice_ptr = start + rank * per * self.frame_bytes
+    self.flags_ptr = start + ((n_bytes + 127) // 128) * 128
+    if world > 32:
+      raise ValueError('PeerFrameBuffer supports up to 32 ranks')
+
+  def render_into(self, dm, ex_dev, params_dev, rotate_first):
+    """Render this rank's frames into its slice of rank 0's buffer and publish a completion flag; on
+    rank 0 the current stream then waits (on the device) until every rank's flag has arrived, so work
+    enqueued after this call sees all the frames.  Returns the full buffer on rank 0, None elsewhere."""
+    import ctypes
+    import torch
+    from . import _lib
+    self.step += 1
+    stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+    if ex_dev.shape[0] > 0:
+      render_device(dm, ex_dev, params_dev, rotate_first, self.res, int(self.slice_ptr))
+    _lib.check(_lib.lib().vp_peer_signal(ctypes.c_void_p(self.flags_ptr + 4 * self.rank), self.step, stream))
+    if self.rank == 0:
+      _lib.check(_lib.lib().vp_peer_wait(ctypes.c_void_p(self.flags_ptr), self.world, self.step, stream))
+    return self.full
+
+  def close(self):
+    from . import _lib
+    if self._base is not None:
+      _lib.lib().vp_ipc_close(self._base)
+      self._base = None
 
 
 _comm_streams = {}
@@ -144,19 +264,22 @@ def _comm_stream(device):
   return _comm_streams[key]
 
 
-def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=None, render_fn=None, n_groups=None):
+def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=None, render_fn=None,
+                            notify_frames=None, gather='p2p'):
   """Frames are independent, so rank r renders frames [r*ceil(T/W), (r+1)*ceil(T/W)) on its own GPU
   with no communication; the only collective is the gather of the uint8 frames to rank 0 (NCCL
-  over NVLink when the group's backend is nccl, issued per group of frames on a side stream so that
-  it overlaps the rendering of the next group; gloo in the CPU tests, which also substitute
+  over NVLink when the group's backend is nccl, issued per chunk of frames on a side stream so that
+  it overlaps the rendering of the next chunk; gloo in the CPU tests, which also substitute
   ``render_fn``).  Returns [T,res,res,3] uint8 on rank 0 (a torch tensor on the group's device)
   and None elsewhere.  The jitter sequence is a function of the global frame index, so every rank
-  generates all of it and slices its shard."""
+  generates all of it and slices its shard.  One identity per call (a clip).
+  gather='p2p' (default): the frames are stored straight into rank 0's buffer over NVLink by the resolve
+  kernel (PeerFrameBuffer); gather='nccl': rendered locally, then gathered with NCCL."""
   import torch
   import torch.distributed as dist
   world = dist.get_world_size(group)
   rank = dist.get_rank(group)
-  coeffs = np.asarray(coeffs, dtype=np.float32)
+  coeffs = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float32))
   t = coeffs.shape[0]
   if isinstance(angles, str):
     if angles != 'jitter':
@@ -167,20 +290,27 @@ def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=N
   use_cuda = dist.get_backend(group) == 'nccl'
   device = torch.device('cuda', torch.cuda.current_device()) if use_cuda else torch.device('cpu')
   local = torch.zeros((per, res, res, 3), dtype=torch.uint8, device=device)
-  shard_angles = None if angles is None else np.asarray(angles)[begin:end]
+  rotate_first = angles is not None
+  shard_angles = coeffs[begin:end, 224:227] if angles is None else np.asarray(angles)[begin:end]
   if use_cuda and render_fn is None:
-    def render_group(a, b):
-      b = min(b, end - begin)
-      if b > a:
-        render_sequence(coeffs[begin + a:begin + b], facemodel, res=res,
-                        angles=None if shard_angles is None else shard_angles[a:b], device=device.index,
-                        out=local[a:b])
-    full = pipelined_gather(render_group, local, per, world, rank, group, n_groups)
+    if len(_identity_runs(coeffs)) != 1:
+      raise ValueError('render_sequence_sharded renders one clip: identity and texture coefficients must not vary')
+    dm = DeviceModel.of(facemodel, device.index)
+    dm.set_identity(coeffs[0:1, :80], coeffs[0:1, 144:224])
+    ex_dev, params_dev = device_inputs(coeffs[begin:end], shard_angles, device)
+    if gather == 'p2p':
+      buf = PeerFrameBuffer(per, res, world, rank, device, group)
+      full = buf.render_into(dm, ex_dev, params_dev, rotate_first)
+      torch.cuda.current_stream(device).synchronize()
+      dist.barrier(group)          # nobody unmaps before every rank's stores are complete
+      buf.close()
+    else:
+      full = pipelined_gather(dm, ex_dev, params_dev, rotate_first, res, local, world, rank, group, notify_frames)
     return None if rank != 0 else full[:t]
   if render_fn is None:
     raise RuntimeError('render_sequence_sharded needs CUDA ranks (nccl backend); there is no CPU path')
   if end > begin:
-    frames = render_fn(coeffs[begin:end], facemodel, res=res, angles=shard_angles)
+    frames = render_fn(coeffs[begin:end], facemodel, res=res, angles=None if angles is None else shard_angles)
     local[:end - begin].copy_(torch.from_numpy(np.ascontiguousarray(frames)))
   gathered = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
   dist.gather(local, gathered, dst=0, group=group)

@@ -214,7 +214,7 @@ def run_ours(args):
     if world == 1:
       render.render_device(dm, ex_dev, params_dev, True, res, frames_dev, mask_dev)
     elif peer is not None:   # every rank's resolve kernel stores straight into rank 0's buffer over NVLink
-      peer.render_into(dm, ex_dev, params_dev, True)
+      peer.render_into(dm, ex_dev, params_dev, True, mode=os.environ.get('VPB200_PEER_MODE', 'auto'))
     else:                    # baseline: render locally, NCCL gather to rank 0
       render.pipelined_gather(dm, ex_dev, params_dev, True, res, frames_dev, world, rank)
 
@@ -231,14 +231,15 @@ def run_ours(args):
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
+  align = torch.zeros(1, dtype=torch.int32, device=dev)
   launches0 = lib.vp_launch_count()
   starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
   ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
   barrier()
   for i in range(args.steps):
-    if world > 1:
-      dist.barrier()
     flush.zero_()                      # L2 flush between timed steps (outside the per-step events)
+    if world > 1:
+      dist.all_reduce(align)           # device-side barrier: every rank's timed step starts together
     starts[i].record()
     step()
     ends[i].record()
@@ -324,7 +325,7 @@ def run_ours(args):
                    'frames_per_gpu': t_local, 'resolution': res,
                    'model': 'synthetic BFM-shaped model, 35709 vertices / 70789 triangles, seed 0', 'coeff_seed': 1,
                    'l2': 'flushed between timed steps (256 MiB write)',
-                   'gather': ('none' if world == 1 else ('frames stored straight into rank 0 buffer over NVLink (CUDA IPC peer memory) by the resolve kernel, device-side completion flags' if peer is not None else 'NCCL gather of uint8 frames to rank 0 inside the step'))},
+                   'gather': ('none' if world == 1 else ('finished chunks of frames pushed into rank 0 buffer over NVLink (CUDA IPC peer memory, copy engine) under the rendering of the next chunk; device-side completion flags' if peer is not None else 'NCCL gather of uint8 frames to rank 0 inside the step'))},
         'roofline': roofline,
         'roofline_pipeline': {'algorithmic_bytes': total_bytes, 'achieved': round(pipeline_gbs, 1), 'peak': peak,
                               'unit': 'GB/s', 'frac': round(pipeline_gbs / peak, 4)},

@@ -75,6 +75,8 @@ int vp_ipc_close(void* base);
  * traps after a bounded spin instead of hanging).  Use an increasing step counter as `value`. */
 int vp_peer_signal(unsigned int* flag_dev, unsigned int value, void* stream);
 int vp_peer_wait(const unsigned int* flags_dev, int n, unsigned int value, void* stream);
+/* Asynchronous device-to-device copy (copy engine), e.g. finished frames -> the peer-mapped buffer. */
+int vp_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * mesh_core_cython replacements: caller-initialised buffers, mutated in place.

@@ -42,7 +42,7 @@ def _worker(rank, world, port, n_frames, res, queue, gather):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('gather', ['p2p', 'nccl'])
+@pytest.mark.parametrize('gather', ['p2p-push', 'p2p-store', 'nccl'])
 def test_two_gpu_shards_equal_single_gpu(gather):
   import torch
   if torch.cuda.device_count() < 2:

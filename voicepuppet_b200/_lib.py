@@ -60,6 +60,7 @@ SIGNATURES = {
     'vp_ipc_export': (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_ulonglong)]),
     'vp_ipc_open': (_i, [_vp, _i, ctypes.POINTER(_vp)]),
     'vp_ipc_close': (_i, [_vp]),
+    'vp_copy_async': (_i, [_vp, _vp, _sz, _vp]),
     'vp_peer_signal': (_i, [_vp, ctypes.c_uint, _vp]),
     'vp_peer_wait': (_i, [_vp, _i, ctypes.c_uint, _vp]),
     'vp_render_colors_core': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),

@@ -44,3 +44,10 @@ extern "C" int vp_peer_wait(const unsigned int* flags_dev, int n, unsigned int v
   VP_LAUNCH_CHECK();
   return VP_OK;
 }
+
+// Copy-engine push of finished frames into the peer-mapped buffer (device-to-device, asynchronous).
+extern "C" int vp_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream) {
+  VP_REQUIRE(bytes == 0 || (dst_dev && src_dev), "null pointer");
+  if (bytes) VP_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return VP_OK;
+}

@@ -206,6 +206,7 @@ class PeerFrameBuffer(object):
     n_bytes = world * per * self.frame_bytes
     self.device = device
     self.step = 0
+    self.local = None
     if rank == 0:
       # frames, then one 32-bit completion flag per rank (128-byte aligned)
       self._storage = torch.zeros(((n_bytes + 127) // 128) * 128 + 128, dtype=torch.uint8, device=device)
@@ -230,20 +231,54 @@ class PeerFrameBuffer(object):
     if world > 32:
       raise ValueError('PeerFrameBuffer supports up to 32 ranks')
 
-  def render_into(self, dm, ex_dev, params_dev, rotate_first):
-    """Render this rank's frames into its slice of rank 0's buffer and publish a completion flag; on
-    rank 0 the current stream then waits (on the device) until every rank's flag has arrived, so work
-    enqueued after this call sees all the frames.  Returns the full buffer on rank 0, None elsewhere."""
+  def render_into(self, dm, ex_dev, params_dev, rotate_first, mode='auto', notify_frames=None):
+    """Render this rank's frames and land them in its slice of rank 0's buffer, then publish a
+    completion flag; on rank 0 the current stream then waits (on the device) until every rank's flag
+    has arrived, so work enqueued after this call sees all the frames.
+      mode='push'  : render into a local staging buffer in chunks; every finished chunk is pushed to
+                     rank 0 by the copy engine on a side stream while the SMs render the next chunk
+      mode='store' : the resolve kernel stores straight into the peer-mapped slice (no staging, no
+                     copy; the kernel then runs at NVLink ingest speed)
+      mode='auto'  : 'store' for two ranks, 'push' beyond (measured on B200: 231 vs 261 us per 75-frame
+                     step at 2 GPUs, 303 vs 272 us at 4; profiles/r01_multigpu.txt)
+    Returns the full buffer on rank 0, None elsewhere."""
     import ctypes
     import torch
     from . import _lib
+    lib = _lib.lib()
+    if mode == 'auto':
+      mode = 'store' if self.world <= 2 else 'push'
     self.step += 1
-    stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-    if ex_dev.shape[0] > 0:
-      render_device(dm, ex_dev, params_dev, rotate_first, self.res, int(self.slice_ptr))
-    _lib.check(_lib.lib().vp_peer_signal(ctypes.c_void_p(self.flags_ptr + 4 * self.rank), self.step, stream))
+    n = ex_dev.shape[0]
+    compute = torch.cuda.current_stream(self.device)
+    cstream = ctypes.c_void_p(compute.cuda_stream)
+    flag = ctypes.c_void_p(self.flags_ptr + 4 * self.rank)
+    if self.rank == 0 or mode == 'store':
+      if n > 0:
+        render_device(dm, ex_dev, params_dev, rotate_first, self.res, int(self.slice_ptr))
+      _lib.check(lib.vp_peer_signal(flag, self.step, cstream))
+    else:
+      if self.local is None:
+        self.local = torch.empty((self.per, self.res, self.res, 3), dtype=torch.uint8, device=self.device)
+      if notify_frames is None:
+        notify_frames = n if n < 48 else -(-n // 3)
+      copy = _comm_stream(self.device)
+      sstream = ctypes.c_void_p(copy.cuda_stream)
+      if n > 0:
+        events = render_device(dm, ex_dev, params_dev, rotate_first, self.res, self.local, notify_frames=notify_frames)
+        for c, ev in enumerate(events):
+          a = c * notify_frames
+          b = min(n, a + notify_frames)
+          copy.wait_event(ev)
+          _lib.check(lib.vp_copy_async(ctypes.c_void_p(self.slice_ptr + a * self.frame_bytes),
+                                       ctypes.c_void_p(self.local.data_ptr() + a * self.frame_bytes),
+                                       (b - a) * self.frame_bytes, sstream))
+      else:
+        copy.wait_stream(compute)
+      _lib.check(lib.vp_peer_signal(flag, self.step, sstream))
+      compute.wait_stream(copy)      # the staging buffer is free again for the next call
     if self.rank == 0:
-      _lib.check(_lib.lib().vp_peer_wait(ctypes.c_void_p(self.flags_ptr), self.world, self.step, stream))
+      _lib.check(lib.vp_peer_wait(ctypes.c_void_p(self.flags_ptr), self.world, self.step, cstream))
     return self.full
 
   def close(self):
@@ -298,9 +333,10 @@ def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=N
     dm = DeviceModel.of(facemodel, device.index)
     dm.set_identity(coeffs[0:1, :80], coeffs[0:1, 144:224])
     ex_dev, params_dev = device_inputs(coeffs[begin:end], shard_angles, device)
-    if gather == 'p2p':
+    if gather in ('p2p', 'p2p-store', 'p2p-push'):
       buf = PeerFrameBuffer(per, res, world, rank, device, group)
-      full = buf.render_into(dm, ex_dev, params_dev, rotate_first)
+      full = buf.render_into(dm, ex_dev, params_dev, rotate_first, mode='store' if gather == 'p2p-store' else ('push' if gather == 'p2p-push' else 'auto'),
+                             notify_frames=notify_frames)
       torch.cuda.current_stream(device).synchronize()
       dist.barrier(group)          # nobody unmaps before every rank's stores are complete
       buf.close()

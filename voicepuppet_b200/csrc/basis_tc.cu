@@ -126,6 +126,24 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
       ptx::mbar_init(bar_accfree + s, kEpiThreads);
     }
     ptx::fence_mbar_init();
+    // The first A tiles do not depend on anything the other warps set up: start the HBM stream now,
+    // under the TMEM allocation and the split of the frame coefficients.
+    for (int p = 0; p < kStagesA; ++p) {
+      const int mp = (int)blockIdx.x + p * (int)gridDim.x;
+      if (mp < ntiles) {
+        uint8_t* dst = smem + kOffAhi + p * kTileA;
+        ptx::mbar_arrive_expect_tx(bar_full + p, kTileA);
+        ptx::tma_load_2d(dst, &tmap_a, 0, mp * kTcM, bar_full + p);
+        ptx::tma_load_2d(dst + kHalfA, &tmap_a, 32, mp * kTcM, bar_full + p);
+      }
+    }
+    for (int p = kStagesA; p < kStagesA + kPrefetchTiles; ++p) {
+      const int mp = (int)blockIdx.x + p * (int)gridDim.x;
+      if (mp < ntiles) {
+        tma_prefetch_2d(&tmap_a, 0, mp * kTcM);
+        tma_prefetch_2d(&tmap_a, 32, mp * kTcM);
+      }
+    }
   }
   if (warp == kWarpMma) {
     ptx::tmem_alloc(tmem_slot, kStagesL * kTcN);
@@ -153,20 +171,12 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
   const int first = blockIdx.x, step = gridDim.x;
 
   if (warp == kWarpTma) {
-    // ===== TMA producer (whole warp loops, one elected lane issues) =====
-    if (elect_one()) {
-      for (int p = 0; p < kPrefetchTiles; ++p) {
-        const int mp = first + p * step;
-        if (mp < ntiles) {
-          tma_prefetch_2d(&tmap_a, 0, mp * kTcM);
-          tma_prefetch_2d(&tmap_a, 32, mp * kTcM);
-        }
-      }
-    }
-    int it = 0;
-    for (int m = first; m < ntiles; m += step, ++it) {
+    // ===== TMA producer (whole warp loops, one elected lane issues); stages 0..kStagesA-1 of the first
+    // round were issued in the prologue =====
+    int it = kStagesA;
+    for (int m = first + kStagesA * step; m < ntiles; m += step, ++it) {
       const int s = it % kStagesA;
-      if (it >= kStagesA) ptx::mbar_wait(bar_afree + s, ((it / kStagesA) - 1) & 1);
+      ptx::mbar_wait(bar_afree + s, ((it / kStagesA) - 1) & 1);
       if (elect_one()) {
         const int mp = m + kPrefetchTiles * step;
         if (mp < ntiles) {

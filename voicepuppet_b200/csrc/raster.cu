@@ -66,12 +66,31 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
                           unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
                           int w, cudaStream_t st) {
   if (ntri == 0 || nframes == 0) return VP_OK;
-  PackedMesh mesh{vrec, triangles, frame_stride};
   static const int fpb_env = [] { const char* e = std::getenv("VPB200_SCATTER_FPB"); return e ? std::atoi(e) : 0; }();
+  static const int legacy = [] { const char* e = std::getenv("VPB200_SCATTER_LEGACY"); return e ? std::atoi(e) : 0; }();
   const int fpb = fpb_env > 0 ? fpb_env : (nframes >= 16 ? 2 : 1);  // frames per block: indices are loaded once
   dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, (nframes + fpb - 1) / fpb);
-  raster_scatter_kernel<kModeColors, PackedMesh, EpochKey><<<grid, kRasterBlock, 0, st>>>(
-      mesh, make_epoch_key(ntri, epoch), keys, tri_color, ntri, nframes, fpb, h, w, 1);
+  const bool fits32 = (unsigned long long)nframes * frame_stride < (1ull << 32) &&
+                      (unsigned long long)nframes * (unsigned long long)ntri < (1ull << 32);
+  if (legacy || !fits32) {  // the generic template on the packed records (kept for A/B measurements)
+    PackedMesh mesh{vrec, triangles, frame_stride};
+    raster_scatter_kernel<kModeColors, PackedMesh, EpochKey><<<grid, kRasterBlock, 0, st>>>(
+        mesh, make_epoch_key(ntri, epoch), keys, tri_color, ntri, nframes, fpb, h, w, 1);
+  } else {
+    ScatterArgs a;
+    a.vrec = vrec;
+    a.tris = triangles;
+    a.keys = keys;
+    a.tri_color = tri_color;
+    a.km = make_epoch_key(ntri, epoch);
+    a.stride = (unsigned)frame_stride;
+    a.ntri = ntri;
+    a.nframes = nframes;
+    a.frames_per_block = fpb;
+    a.h = h;
+    a.w = w;
+    raster_scatter_packed_kernel<<<grid, kRasterBlock, 0, st>>>(a);
+  }
   VP_LAUNCH_CHECK();
   return VP_OK;
 }

@@ -199,6 +199,137 @@ raster_scatter_kernel(Mesh mesh, KeyMaker km, unsigned long long* __restrict__ k
   }
 }
 
+// ---- fused-path scatter (render_colors semantics, packed records, epoch keys) ----------------
+// Same arithmetic as raster_scatter_kernel<kModeColors, PackedMesh, EpochKey> with const_init, written
+// for the instruction-issue limit that bounds it (ncu r01d: 75 % issue-active, 365 warp-instructions per
+// 32 triangles): uniform per-frame base pointers, a bounding box without the x86-cast emulation when
+// every coordinate is finite and small (the emulation only matters for NaN / |x| >= 2^31), byte-lane
+// arithmetic for the flat colour, and one flat pixel loop per lane.
+struct ScatterArgs {
+  const float4* vrec;           // [frames][stride]
+  const int4* tris;             // [ntri]
+  unsigned long long* keys;     // [frames][h*w]
+  uint32_t* tri_color;          // [frames][ntri]
+  EpochKey km;
+  unsigned stride;              // float4 per frame
+  int ntri, nframes, frames_per_block, h, w;
+};
+
+// (a + b + c) / 3 per byte lane of three packed RGBx words; sums <= 765, so x * 0x5556 >> 16 == x / 3.
+__device__ __forceinline__ uint32_t flat_color_packed(uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t rb = (a & 0x00FF00FFu) + (b & 0x00FF00FFu) + (c & 0x00FF00FFu);  // R | B << 16 (10 bits each)
+  const uint32_t g = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu);
+  const uint32_t r3 = ((rb & 0xFFFFu) * 0x5556u) >> 16;
+  const uint32_t b3 = ((rb >> 16) * 0x5556u) & 0xFFFF0000u;
+  const uint32_t g3 = ((g * 0x5556u) >> 8) & 0xFF00u;
+  return r3 | g3 | b3 | 0xFF000000u;
+}
+
+__global__ void __launch_bounds__(kRasterBlock)
+raster_scatter_packed_kernel(const ScatterArgs a) {
+  __shared__ Candidate s_big[kRasterBlock / 32];
+  const int f = blockIdx.x * kRasterBlock + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const bool valid = f < a.ntri;
+  int4 t = make_int4(0, 0, 0, 0);
+  if (valid) t = __ldg(a.tris + f);  // shared by all the frames this block walks
+  const unsigned long long low = static_cast<unsigned long long>(a.km.tri_mask - (uint32_t)t.w);
+  const int wm1 = a.w - 1, hm1 = a.h - 1;
+  const unsigned npix = (unsigned)a.h * (unsigned)a.w;
+
+  const int frame_begin = blockIdx.y * a.frames_per_block;
+  const int frame_end = min(a.nframes, frame_begin + a.frames_per_block);
+  for (int frame = frame_begin; frame < frame_end; ++frame) {
+    // 32-bit element offsets (the launcher checks nframes * stride and nframes * ntri fit)
+    const unsigned vbase = (unsigned)frame * a.stride;
+    unsigned long long* keys = a.keys + (size_t)frame * npix;
+    Candidate c;
+    c.n = 0;
+    c.key = 0ull;
+    c.id = 0;
+    c.z0 = c.z1 = c.z2 = 0.f;
+    if (valid) {
+      const float4 v0 = __ldg(a.vrec + (vbase + (unsigned)t.x)), v1 = __ldg(a.vrec + (vbase + (unsigned)t.y)),
+                   v2 = __ldg(a.vrec + (vbase + (unsigned)t.z));
+      a.tri_color[(unsigned)frame * (unsigned)a.ntri + (unsigned)f] =
+          flat_color_packed(__float_as_uint(v0.w), __float_as_uint(v1.w), __float_as_uint(v2.w));
+      const float kBig = 1073741824.0f;  // 2^30: below it ceil/floor and the int casts are exact and in range
+      const bool tame = fabsf(v0.x) < kBig && fabsf(v1.x) < kBig && fabsf(v2.x) < kBig && fabsf(v0.y) < kBig &&
+                        fabsf(v1.y) < kBig && fabsf(v2.y) < kBig;  // false for NaN / inf
+      bool nonempty;
+      if (tame) {
+        // mesh_core.cpp:194-203 for finite coordinates: min / max are order independent, the casts exact
+        c.s.x_lo = max(__float2int_ru(fminf(v0.x, fminf(v1.x, v2.x))), 0);
+        c.s.x_hi = min(__float2int_rd(fmaxf(v0.x, fmaxf(v1.x, v2.x))), wm1);
+        c.s.y_lo = max(__float2int_ru(fminf(v0.y, fminf(v1.y, v2.y))), 0);
+        c.s.y_hi = min(__float2int_rd(fmaxf(v0.y, fmaxf(v1.y, v2.y))), hm1);
+        nonempty = c.s.x_hi >= c.s.x_lo && c.s.y_hi >= c.s.y_lo;
+      } else {
+        nonempty = tri_bbox(c.s, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, a.h, a.w);
+      }
+      if (nonempty) {
+        const float d = flat_depth(v0.z, v1.z, v2.z);
+        if (d > kInitDepth) {  // mesh_core.cpp:211 against the constant initial depth; false for NaN
+          c.n = (c.s.x_hi - c.s.x_lo + 1) * (c.s.y_hi - c.s.y_lo + 1);
+          const uint32_t b = __float_as_uint(__fadd_rn(d, 0.0f));  // -0 -> +0
+          const uint32_t code = b ^ (static_cast<uint32_t>(static_cast<int>(b) >> 31) | 0x80000000u);
+          c.key = a.km.epoch_field | (static_cast<unsigned long long>(code) << a.km.tri_bits) | low;
+          tri_edges(c.s, v0.x, v0.y, v1.x, v1.y, v2.x, v2.y);
+        }
+      }
+    }
+
+    if (c.n > 0 && c.n <= kSmallBox) {
+      // one flat loop over the box: row terms are refreshed when x wraps
+      int x = c.s.x_lo, y = c.s.y_lo;
+      float py = VP_SUB(static_cast<float>(y), c.s.ay);
+      float m0y = VP_MUL(c.s.e0y, py), m1y = VP_MUL(c.s.e1y, py);
+      unsigned long long* row = keys + (unsigned)y * (unsigned)a.w;
+#pragma unroll 1
+      for (int i = 0; i < c.n; ++i) {
+        const float px = VP_SUB(static_cast<float>(x), c.s.ax);
+        const float d02 = VP_ADD(VP_MUL(c.s.e0x, px), m0y);
+        const float d12 = VP_ADD(VP_MUL(c.s.e1x, px), m1y);
+        const float u = VP_MUL(VP_SUB(VP_MUL(c.s.d11, d02), VP_MUL(c.s.d01, d12)), c.s.inv);
+        const float v = VP_MUL(VP_SUB(VP_MUL(c.s.d00, d12), VP_MUL(c.s.d01, d02)), c.s.inv);
+        if (uv_inside(u, v)) atomicMax(row + x, c.key);
+        if (++x > c.s.x_hi) {
+          x = c.s.x_lo;
+          ++y;
+          py = VP_SUB(static_cast<float>(y), c.s.ay);
+          m0y = VP_MUL(c.s.e0y, py);
+          m1y = VP_MUL(c.s.e1y, py);
+          row += a.w;
+        }
+      }
+    }
+    unsigned big = __ballot_sync(0xFFFFFFFFu, c.n > kSmallBox);
+    if (big) {
+      FullKey unused{};
+      Candidate* slot = &s_big[threadIdx.x >> 5];
+      while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        __syncwarp();
+        if ((int)lane == src) *slot = c;
+        __syncwarp();
+        const Candidate o = *slot;
+        const int bw = o.s.x_hi - o.s.x_lo + 1;
+        if (bw >= 16) {  // wide box: the warp strides along x, row by row
+          for (int y = o.s.y_lo; y <= o.s.y_hi; ++y)
+            offer_span<kModeColors>(o, unused, y, o.s.x_lo + (int)lane, o.s.x_hi, 32, keys, a.h, a.w);
+        } else {         // narrow box: 32 / bw' rows at a time (bw' = bw rounded up to a power of two)
+          const int bwp = bw <= 1 ? 1 : (bw <= 2 ? 2 : (bw <= 4 ? 4 : (bw <= 8 ? 8 : 16)));
+          const int rows_per_iter = 32 / bwp;
+          const int dx = (int)lane & (bwp - 1), dy = (int)lane / bwp;
+          for (int y = o.s.y_lo + dy; y <= o.s.y_hi; y += rows_per_iter)
+            if (dx < bw) offer_span<kModeColors>(o, unused, y, o.s.x_lo + dx, o.s.x_lo + dx, 1, keys, a.h, a.w);
+        }
+      }
+    }
+  }
+}
+
 // keys[p] = init_key(depth[p]) for the caller-initialised depth buffer.
 __global__ void keys_from_depth_kernel(const float* __restrict__ depth, unsigned long long* __restrict__ keys,
                                        size_t n) {

@@ -165,7 +165,7 @@ int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
 //      raster record (x, S - y, -z, rgb bytes) and/or the reference's per-vertex outputs.
 // Shared memory is double buffered across frames, so a frame costs two block barriers.
 // =========================================================================================
-struct FrameShared {   // per-frame constants staged in shared memory
+struct __align__(16) FrameShared {   // per-frame constants staged in shared memory
   FrameParams par;     // 192 B: rotation (float64), translation, gamma
   float rot[12];       // rotation as float32
   float sh[28];        // gamma with the SH band constants (and the 0.8 ambient) folded in: [3][9]
@@ -223,10 +223,15 @@ __global__ void frame_prep_kernel(const FrameParams* __restrict__ params, FrameS
   }
 }
 
-__global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs a) {
+// Frame loop, software pipelined over double-buffered shared memory so that a frame costs ONE block
+// barrier: iteration f computes the triangle normals of frame f (positions staged by iteration f-1),
+// stages the positions of frame f+1, synchronises, then finishes the own vertex of frame f, whose
+// shared-memory reads are independent of the next iteration's writes (the other buffers).
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_tile_kernel(const VertexArgs a) {
   __shared__ float4 s_pos[2][kTileLV];
-  __shared__ float4 s_fn[kTileLT + 1];
-  __shared__ FrameShared s_frame[2];
+  __shared__ float4 s_fn[2][kTileLT + 1];
+  __shared__ __align__(16) FrameShared s_frame[3];  // read after the barrier, restaged two iterations later
   static_assert(sizeof(FrameParams) == 192, "FrameParams layout");
 
   const TileDesc td = a.tiles[blockIdx.x];
@@ -259,6 +264,8 @@ __global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs
       }
     }
   }
+  // triangle corners as byte offsets into a position buffer (3 x 10-bit local indices << 4 fit 3 x 14 bits:
+  // kept as the packed word, decoded with one shift-and-mask per corner)
   uint32_t lt[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -266,11 +273,19 @@ __global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs
     lt[q] = (j < td.nlt) ? __ldg(a.ltri + td.ltri_off + j) : 0u;
   }
   const bool own = tid < td.nv;
-  uint4 rg = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  // ring slots as byte offsets into a normal buffer, two 16-bit halves per word; pad slots point at the
+  // zero entry kTileLT (the zero row the reference appends, reconstruct_mesh.py:47-48)
+  uint32_t ro[4] = {0, 0, 0, 0};
   float tr = 0.f, tg = 0.f, tb = 0.f;
   int orig = 0;
   if (own) {
-    rg = __ldg(reinterpret_cast<const uint4*>(a.ring) + gv[0]);
+    const uint4 rg = __ldg(reinterpret_cast<const uint4*>(a.ring) + gv[0]);
+    const uint32_t w[4] = {rg.x, rg.y, rg.z, rg.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lo = min(w[k] & 0xFFFFu, (uint32_t)kTileLT), hi = min(w[k] >> 16, (uint32_t)kTileLT);
+      ro[k] = (lo << 4) | (hi << 20);
+    }
     if (a.tex) {
       tr = __ldg(a.tex + 3 * (size_t)gv[0]);
       tg = __ldg(a.tex + 3 * (size_t)gv[0] + 1);
@@ -278,67 +293,79 @@ __global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs
     }
     orig = __ldg(a.v_int2orig + gv[0]);
   }
-  if (tid == 0) s_fn[kTileLT] = make_float4(0.f, 0.f, 0.f, 0.f);  // what pad slots of the ring read
+  if (tid < 2) s_fn[tid][kTileLT] = make_float4(0.f, 0.f, 0.f, 0.f);  // what pad slots of the ring read
 
   const int f_begin = blockIdx.y * a.frames_per_block;
   const int f_end = min(a.nframes, f_begin + a.frames_per_block);
+  if (f_begin >= f_end) return;
 
-  // displacement of the first frame (software pipelined: frame f+1 is fetched while f is computed)
   float dx[3], dy[3], dz[3];
 #pragma unroll
   for (int q = 0; q < 3; ++q) dx[q] = dy[q] = dz[q] = 0.f;
-  if (a.disp && f_begin < f_end) {
+  auto fetch_disp = [&](int f) {  // expression displacement of this thread's local vertices in frame f
+    if (a.disp == nullptr) return;
 #pragma unroll
     for (int q = 0; q < 3; ++q)
       if (q < nq_v) {
-        const float* d = a.disp + (size_t)f_begin * a.disp_stride + 3 * (size_t)gv[q];
+        const float* d = a.disp + (size_t)f * a.disp_stride + 3 * (size_t)gv[q];
         dx[q] = __ldg(d);
         dy[q] = __ldg(d + 1);
         dz[q] = __ldg(d + 2);
       }
-  }
-
-  for (int f = f_begin; f < f_end; ++f) {
-    const int buf = (f - f_begin) & 1;
-    FrameShared& fs = s_frame[buf];
-    // ---- phase 1: per-frame constants and local positions -> shared memory ----------------
+  };
+  auto stage = [&](int f, int buf) {  // per-frame constants and local positions of frame f -> shared memory
     if (tid < (int)(sizeof(FrameShared) / 4))
-      reinterpret_cast<uint32_t*>(&fs)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.fshared + f) + tid);
+      reinterpret_cast<uint32_t*>(&s_frame[(f - f_begin) % 3])[tid] =
+          __ldg(reinterpret_cast<const uint32_t*>(a.fshared + f) + tid);
 #pragma unroll
     for (int q = 0; q < 3; ++q)
       if (q < nq_v) s_pos[buf][tid + q * kTileV] = make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
-    const double own_x = bx + (double)dx[0], own_y = by + (double)dy[0], own_z = bz + (double)dz[0];
-    if (a.disp && f + 1 < f_end) {
+  };
+
+  // prologue: frame f_begin staged, frame f_begin + 1 in flight
+  fetch_disp(f_begin);
+  stage(f_begin, 0);
+  double own_x = bx + (double)dx[0], own_y = by + (double)dy[0], own_z = bz + (double)dz[0];
+  if (f_begin + 1 < f_end) fetch_disp(f_begin + 1);
+  __syncthreads();
+
+  for (int f = f_begin; f < f_end; ++f) {
+    const int buf = (f - f_begin) & 1;
+    // ---- triangle normals of frame f (reconstruct_mesh.py:41-46) ---------------------------
+    {
+      const char* pos = reinterpret_cast<const char*>(s_pos[buf]);
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
-        if (q < nq_v) {
-          const float* d = a.disp + (size_t)(f + 1) * a.disp_stride + 3 * (size_t)gv[q];
-          dx[q] = __ldg(d);
-          dy[q] = __ldg(d + 1);
-          dz[q] = __ldg(d + 2);
+      for (int q = 0; q < 4; ++q)
+        if (q < nq_t) {
+          const float4 p1 = *reinterpret_cast<const float4*>(pos + ((lt[q] << 4) & 0x3FF0u)),
+                       p2 = *reinterpret_cast<const float4*>(pos + ((lt[q] >> 6) & 0x3FF0u)),
+                       p3 = *reinterpret_cast<const float4*>(pos + ((lt[q] >> 16) & 0x3FF0u));
+          const float e1x = p1.x - p2.x, e1y = p1.y - p2.y, e1z = p1.z - p2.z;
+          const float e2x = p2.x - p3.x, e2y = p2.y - p3.y, e2z = p2.z - p3.z;
+          s_fn[buf][tid + q * kTileV] =
+              make_float4(e1y * e2z - e1z * e2y, e1z * e2x - e1x * e2z, e1x * e2y - e1y * e2x, 0.f);
         }
     }
-    __syncthreads();
-    // ---- phase 2: triangle normals (reconstruct_mesh.py:41-46) ----------------------------
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < nq_t) {
-        const float4 p1 = s_pos[buf][lt[q] & 1023u], p2 = s_pos[buf][(lt[q] >> 10) & 1023u],
-                     p3 = s_pos[buf][(lt[q] >> 20) & 1023u];
-        const float e1x = p1.x - p2.x, e1y = p1.y - p2.y, e1z = p1.z - p2.z;
-        const float e2x = p2.x - p3.x, e2y = p2.y - p3.y, e2z = p2.z - p3.z;
-        s_fn[tid + q * kTileV] = make_float4(e1y * e2z - e1z * e2y, e1z * e2x - e1x * e2z, e1x * e2y - e1y * e2x, 0.f);
-      }
+    // ---- stage frame f + 1 (other buffers), fetch frame f + 2 --------------------------------
+    const double cur_x = own_x, cur_y = own_y, cur_z = own_z;
+    if (f + 1 < f_end) {
+      stage(f + 1, buf ^ 1);
+      own_x = bx + (double)dx[0];
+      own_y = by + (double)dy[0];
+      own_z = bz + (double)dz[0];
+      if (f + 2 < f_end) fetch_disp(f + 2);
+    }
     __syncthreads();
     if (!own) continue;
-    // ---- phase 3: the own vertex ----------------------------------------------------------
+    // ---- the own vertex of frame f -----------------------------------------------------------
+    const FrameShared& fs = s_frame[(f - f_begin) % 3];
     float nx = 0.f, ny = 0.f, nz = 0.f;
     {
-      const uint32_t w[4] = {rg.x, rg.y, rg.z, rg.w};
+      const char* fnb = reinterpret_cast<const char*>(s_fn[buf]);
 #pragma unroll
       for (int s = 0; s < VP_RING; ++s) {
-        const uint32_t j = min((w[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu, (uint32_t)kTileLT);
-        const float4 fn = s_fn[j];
+        const uint32_t off = (s & 1) ? (ro[s >> 1] >> 16) : (ro[s >> 1] & 0xFFFFu);
+        const float4 fn = *reinterpret_cast<const float4*>(fnb + off);
         nx += fn.x;
         ny += fn.y;
         nz += fn.z;
@@ -369,7 +396,7 @@ __global__ void __launch_bounds__(kTileV, 6) vertex_tile_kernel(const VertexArgs
 
     // geometry in float64
     const double* R = fs.par.rot;
-    double sx = own_x, sy = own_y, sz = own_z;
+    double sx = cur_x, sy = cur_y, sz = cur_z;
     if (a.rotate_first) {  // Reconstruction_rotation rotates the shape before projecting it (:211)
       double tx, ty, tz;
       rotate_row(R, sx, sy, sz, tx, ty, tz);
@@ -434,7 +461,12 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.fshared = fshared;
   a.nframes = nframes;
   static const int fpb_env = [] { const char* e = std::getenv("VPB200_VERTEX_FPB"); return e ? std::atoi(e) : 0; }();
-  a.frames_per_block = fpb_env > 0 ? fpb_env : (nframes >= 16 ? 4 : 1);
+  // One resident wave: the tile constants (dependent global loads) and the pipeline prologue are paid
+  // once per CTA, so each CTA takes as many frames as keeps the grid within the 6 CTAs/SM that fit.
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  const int groups = std::max(1, std::min(nframes, (sms * 6) / std::max(m->ntiles, 1)));
+  a.frames_per_block = fpb_env > 0 ? fpb_env : (nframes + groups - 1) / groups;
   a.rotate_first = rotate_first;
   a.has_out = (out.shape || out.norm || out.color || out.proj || out.zbuf) ? 1 : 0;
   a.focal = focal;
@@ -446,7 +478,13 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.out = out;
   a.nver = m->nver;
   dim3 grid(m->ntiles, (nframes + a.frames_per_block - 1) / a.frames_per_block);
-  vertex_tile_kernel<<<grid, kTileV, 0, st>>>(a);
+  static const int minb_env = [] { const char* e = std::getenv("VPB200_VERTEX_MINB"); return e ? std::atoi(e) : 0; }();
+  if (minb_env == 5)
+    vertex_tile_kernel<5><<<grid, kTileV, 0, st>>>(a);
+  else if (minb_env == 7)
+    vertex_tile_kernel<7><<<grid, kTileV, 0, st>>>(a);
+  else
+    vertex_tile_kernel<6><<<grid, kTileV, 0, st>>>(a);
   VP_LAUNCH_CHECK();
   return VP_OK;
 }

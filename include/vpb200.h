@@ -130,19 +130,26 @@ int vp_model_ntiles(const vp_model* m);
  * tables against Compute_norm (reconstruct_mesh.py:35-52).
  *   tri[ntri][3], point_buf[nver][8] 0-based (pad = anything outside [0, ntri)), xyz[nver][3].
  * vp_topology_copy: v_int2orig[nver], tri_int[ntri][4] (internal a,b,c + original index),
- *   tiles[ntiles][6] (v_begin, nv, nlv, nlt, halo_off, ltri_off), ltri[nltri] (3 x 10-bit local
- *   vertex ids), halo[nhalo] (internal vertex ids), ring[nver][8] (local triangle id, 0xFFFF pad). */
+ *   tiles[ntiles][7] (v_begin, nv, nlv, nlt, halo_off, ltri_off, fan), ltri[nltri] (3 x 10-bit local
+ *   vertex ids), halo[nhalo] (internal vertex ids), ring[nver][8] (local triangle id, 0xFFFF pad),
+ *   fan[nver][5] (tiles with fan = 1: byte offsets (local vertex * 16) of the ring vertices u0..u8, two per
+ *   word, and in the top half of word 4 the mask of the pairs (u_i, u_i+1) that are faces of the vertex). */
 typedef struct vp_topology vp_topology;
 int vp_topology_build(vp_topology** out, int nver, int ntri, const int* tri, const int* point_buf,
                       const double* xyz);
 void vp_topology_destroy(vp_topology* t);
 int vp_topology_sizes(const vp_topology* t, int* ntiles, int* nltri, int* nhalo);
 int vp_topology_copy(const vp_topology* t, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
-                     int* halo, uint16_t* ring);
+                     int* halo, uint16_t* ring, uint32_t* fan);
 
 /* Expression-basis kernel selection: 0 = automatic (FP32 streamed kernel below 16 frames per launch,
  * tcgen05 3xTF32 GEMM from 16 frames up), 1 = always FP32 SIMT, 2 = always tcgen05 3xTF32. */
 int vp_set_basis_mode(vp_model* m, int mode);
+
+/* Vertex-normal path selection: 0 = automatic (fan records where the mesh chains into fans, the generic
+ * ring-of-faces kernel elsewhere), 1 = always the generic kernel (tests compare the two). */
+int vp_set_vertex_mode(vp_model* m, int mode);
+int vp_model_fan_tiles(const vp_model* m); /* tiles that take the fan path (of vp_model_ntiles) */
 
 /* Per-clip constants ("identity mean precomputed once"): base shape = meanshape + idBase.id
  * - center, texture = meantex + texBase.tex.  Either pointer may be NULL to keep the old one. */

@@ -139,3 +139,61 @@ def test_tensor_core_basis_matches_fp32_and_fp64(full_model, t):
     err = float(np.abs(out[mode] - want).max())
     assert err < 4e-7 * max(1.0, disp_scale), (mode, err)      # fp32-grade accuracy of the displacement
   assert float(np.abs(out[1] - out[2]).max()) < 4e-7
+
+
+def test_generic_vertex_kernel_matches_fan_kernel(full_model):
+  """K2 has two flavours (fan records / ring of staged face normals); the full model is manifold, so it
+  normally takes the fan path: force the generic kernel and compare both with the oracle."""
+  from voicepuppet_b200 import _lib
+  from voicepuppet_b200.model import DeviceModel
+  dm = DeviceModel.of(full_model)
+  lib = _lib.lib()
+  assert lib.vp_model_fan_tiles(dm.handle) == lib.vp_model_ntiles(dm.handle)
+  coeffs = synthetic.make_coeffs(2, seed=9)
+  jit = orc.jitter_angle_sequence(2)
+  want = orc.reconstruction_rotation(coeffs[1:2], full_model, jit[1])
+  fan = rm.Reconstruction_rotation(coeffs[1:2], full_model, jit[1])
+  try:
+    _lib.check(lib.vp_set_vertex_mode(dm.handle, 1))
+    gen = rm.Reconstruction_rotation(coeffs[1:2], full_model, jit[1])
+  finally:
+    _lib.check(lib.vp_set_vertex_mode(dm.handle, 0))
+  for name, a, b, c in zip(NAMES7[:6], fan, gen, want):
+    assert rel_err(a, c) <= REL and rel_err(b, c) <= REL, name
+  assert rel_err(fan[2], gen[2]) <= 2e-6      # colours: same normals up to float32 summation order
+
+
+def test_awkward_mesh_takes_the_generic_path():
+  """A triangle soup with isolated vertices, duplicate and misplaced point_buf entries does not chain into
+  fans: the generic kernel must reproduce Compute_norm's slot-order ring sum (NaN normals included)."""
+  from voicepuppet_b200 import _lib
+  from voicepuppet_b200.model import DeviceModel
+  rng = np.random.Generator(np.random.PCG64(3))
+  nver, ntri = 700, 1500
+  tri = rng.integers(0, nver - 20, (ntri, 3))
+  pb = np.full((nver, 8), ntri, dtype=np.int64)
+  fill = np.zeros(nver, dtype=np.int64)
+  for f in range(ntri):
+    for v in tri[f]:
+      if fill[v] < 8:
+        pb[v, fill[v]] = f
+        fill[v] += 1
+  pb[5, 0], pb[5, 3] = ntri, pb[5, 0]
+  pb[6, 1] = pb[6, 0]
+  pb[7, 2] = pb[400, 0]                                   # a face that does not contain the vertex
+  pts = rng.random((nver, 3)) * 0.5
+  model = synthetic.SyntheticBFM(
+      meanshape=pts.reshape(1, -1).astype(np.float32), idBase=(rng.standard_normal((3 * nver, 80)) * 1e-3).astype(np.float32),
+      exBase=(rng.standard_normal((3 * nver, 64)) * 1e-3).astype(np.float32),
+      meantex=np.full((1, 3 * nver), 128, np.float32), texBase=rng.standard_normal((3 * nver, 80)).astype(np.float32),
+      point_buf=(pb + 1).astype(np.float64), tri=(tri + 1).astype(np.float64), keypoints=np.arange(68, dtype=np.int32))
+  dm = DeviceModel.of(model)
+  lib = _lib.lib()
+  assert lib.vp_model_fan_tiles(dm.handle) < lib.vp_model_ntiles(dm.handle)
+  c = synthetic.make_coeffs(1, seed=2)
+  got = rm.Reconstruction(c, model)
+  want = orc.reconstruction(c, model)
+  for name, a, b in zip(NAMES7, got, want):
+    assert np.array_equal(np.isnan(a), np.isnan(b)), name
+    assert rel_err(np.nan_to_num(a), np.nan_to_num(b)) <= REL, (name, rel_err(np.nan_to_num(a), np.nan_to_num(b)))
+  assert np.isnan(want[2]).any()                          # isolated vertices: 0/0 normals -> NaN colours

@@ -10,7 +10,7 @@ import pytest
 from oracle import reconstruct_oracle as orc
 from voicepuppet_b200 import _lib, synthetic
 
-TILE_V, TILE_LV, TILE_LT = 128, 384, 512
+TILE_V, TILE_LV, TILE_LT = 128, 256, 512
 
 
 def build(model):
@@ -24,21 +24,44 @@ def build(model):
   nt, nl, nh = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
   _lib.check(lib.vp_topology_sizes(h, ctypes.byref(nt), ctypes.byref(nl), ctypes.byref(nh)))
   t = dict(v_int2orig=np.zeros(nver, np.int32), tri_int=np.zeros((tri.shape[0], 4), np.int32),
-           tiles=np.zeros((nt.value, 6), np.int32), ltri=np.zeros(nl.value, np.uint32),
-           halo=np.zeros(nh.value, np.int32), ring=np.zeros((nver, 8), np.uint16))
-  _lib.check(lib.vp_topology_copy(h, *[_lib.ptr(t[k]) for k in ('v_int2orig', 'tri_int', 'tiles', 'ltri', 'halo', 'ring')]))
+           tiles=np.zeros((nt.value, 7), np.int32), ltri=np.zeros(nl.value, np.uint32),
+           halo=np.zeros(nh.value, np.int32), ring=np.zeros((nver, 8), np.uint16),
+           fan=np.zeros((nver, 5), np.uint32))
+  _lib.check(lib.vp_topology_copy(h, *[_lib.ptr(t[k]) for k in ('v_int2orig', 'tri_int', 'tiles', 'ltri', 'halo', 'ring', 'fan')]))
   lib.vp_topology_destroy(h)
   return t, tri, pb
 
 
-def normals_from_tiles(t, shape_orig):
-  """What vertex_tile_kernel does for the normals, in float64."""
+def fan_normals(fan, pos, nv):
+  """What vertex_fan_kernel does: sum over the set mask bits of (u_i - v) x (u_i+1 - v)."""
+  fan = fan.astype(np.int64)
+  off = np.stack([fan[:, 0] & 0xFFFF, fan[:, 0] >> 16, fan[:, 1] & 0xFFFF, fan[:, 1] >> 16, fan[:, 2] & 0xFFFF,
+                  fan[:, 2] >> 16, fan[:, 3] & 0xFFFF, fan[:, 3] >> 16, fan[:, 4] & 0xFFFF], axis=1)
+  assert np.all(off % 16 == 0)
+  u = off // 16
+  mask = fan[:, 4] >> 16
+  acc = np.zeros((nv, 3))
+  v = pos[:nv]
+  for i in range(8):
+    on = ((mask >> i) & 1).astype(bool)
+    acc[on] += np.cross(pos[u[on, i]] - v[on], pos[u[on, i + 1]] - v[on])
+  return acc
+
+
+def normals_from_tiles(t, shape_orig, force_generic=False):
+  """What the vertex kernels do for the normals (fan tiles: vertex_fan_kernel, the others:
+  vertex_tile_kernel), in float64."""
   nver = shape_orig.shape[0]
   shape_int = shape_orig[t['v_int2orig']]
   out = np.zeros((nver, 3))
-  for v_begin, nv, nlv, nlt, halo_off, ltri_off in t['tiles']:
+  for v_begin, nv, nlv, nlt, halo_off, ltri_off, is_fan in t['tiles']:
     local = np.concatenate([np.arange(v_begin, v_begin + nv), t['halo'][halo_off:halo_off + nlv - nv]])
     pos = shape_int[local]
+    if is_fan and not force_generic:
+      acc = fan_normals(t['fan'][v_begin:v_begin + nv], pos, nv)
+      with np.errstate(invalid='ignore', divide='ignore'):
+        out[t['v_int2orig'][v_begin:v_begin + nv]] = acc / np.linalg.norm(acc, axis=1, keepdims=True)
+      continue
     lt = t['ltri'][ltri_off:ltri_off + nlt]
     a, b, c = lt & 1023, (lt >> 10) & 1023, (lt >> 20) & 1023
     fn = np.cross(pos[a] - pos[b], pos[b] - pos[c]) if nlt else np.zeros((0, 3))
@@ -71,9 +94,11 @@ def check_model(model):
   coeff = synthetic.make_coeffs(1, seed=5)
   shape = orc.shape_formation(coeff[:, :80], coeff[:, 80:144], model)
   want = orc.compute_norm(shape, model)[0]
-  got = normals_from_tiles(t, shape[0].astype(np.float64))
-  both_nan = np.isnan(want) & np.isnan(got)
-  assert np.allclose(np.where(both_nan, 0, got), np.where(both_nan, 0, want), rtol=0, atol=1e-12)
+  for force_generic in (False, True):   # the ring tables stay valid for fan tiles too
+    got = normals_from_tiles(t, shape[0].astype(np.float64), force_generic)
+    both_nan = np.isnan(want) & np.isnan(got)
+    assert np.array_equal(np.isnan(want), np.isnan(got))
+    assert np.allclose(np.where(both_nan, 0, got), np.where(both_nan, 0, want), rtol=0, atol=1e-12)
   return t
 
 
@@ -86,7 +111,8 @@ def test_full_model_tiles(full_model):
   tiles = t['tiles']
   # spatial order works: tiles are nearly full and the halo stays small
   assert tiles.shape[0] <= 300
-  assert tiles[:, 2].mean() < 260
+  assert tiles[:, 2].mean() < 220
+  assert tiles[:, 6].all()        # a manifold mesh: every tile takes the fan path
 
 
 def test_awkward_meshes():
@@ -109,7 +135,8 @@ def test_awkward_meshes():
       exBase=np.zeros((3 * nver, 64), np.float32), meantex=np.zeros((1, 3 * nver), np.float32),
       texBase=np.zeros((3 * nver, 80), np.float32), point_buf=(pb + 1).astype(np.float64),
       tri=(tri + 1).astype(np.float64), keypoints=np.arange(68, dtype=np.int32))
-  check_model(model)
+  t = check_model(model)
+  assert not t['tiles'][:, 6].all()  # a triangle soup does not chain into fans: generic tiles
 
 
 def test_rejects_bad_indices():

@@ -28,7 +28,7 @@ int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_co
 
 // ---- vertex-tile topology (topology.cpp builds it, reconstruct.cu consumes it) ----------
 constexpr int kTileV = 128;    // max own vertices per tile == threads per CTA of the vertex kernel
-constexpr int kTileLV = 384;   // max own + halo vertices
+constexpr int kTileLV = 256;   // max own + halo vertices (two staging slots per thread)
 constexpr int kTileLT = 512;   // max triangles touching the tile's own vertices
 constexpr uint16_t kRingPad = 0xFFFF;
 
@@ -39,7 +39,16 @@ struct TileDesc {
   int nlt;       // local triangles
   int halo_off;  // into halo[] (internal vertex ids of local vertices nv..nlv-1)
   int ltri_off;  // into ltri[] (3 x 10-bit local vertex indices)
+  int fan;       // 1: every own vertex has a fan record (see Topology::fan), 0: generic ring-of-faces path
 };
+
+// Fan record of one vertex v: up to 9 tile-local vertices u0..u8 such that every face point_buf lists for
+// v is (v, u_i, u_i+1) in the triangle's cyclic order for the i whose bit is set in `mask`; then
+// sum of face normals = sum over set bits of (u_i - v) x (u_i+1 - v), which needs 9 position gathers
+// instead of a staged pass over the tile's triangles plus 8 normal gathers.  Five words: byte offsets
+// (local index * 16) of u_2k | u_2k+1 << 16 for k = 0..3, then u_8 | mask << 16.  Unused entries name v.
+constexpr int kFanWords = 5;
+constexpr int kFanEntries = 9;
 
 // Host-side result of the one-off mesh analysis (topology.cpp).
 struct Topology {
@@ -50,6 +59,7 @@ struct Topology {
   std::vector<uint32_t> ltri;
   std::vector<int> halo;
   std::vector<uint16_t> ring;      // [nver][8] in internal vertex order
+  std::vector<uint32_t> fan;       // [nver][kFanWords] in internal vertex order (zeros where the tile is generic)
 };
 
 // tri: [ntri][3] 0-based original vertex ids; point_buf: [nver][8] 0-based original triangle ids
@@ -95,6 +105,9 @@ struct vp_model {
   uint32_t* ltri = nullptr;
   int* halo = nullptr;
   uint16_t* ring = nullptr;     // [nver][8] local triangle index per point_buf slot
+  uint32_t* fan = nullptr;      // [nver][5] fan records (tiles with TileDesc::fan)
+  int* tile_list = nullptr;     // tile ids: the n_fan_tiles fan tiles first, then the generic ones
+  int n_fan_tiles = 0;
   // TMA descriptor of exb for the tcgen05 basis kernel (a CUtensorMap, kept opaque here)
   alignas(64) unsigned char tmap_exb[128] = {0};
   bool have_tmap = false;
@@ -111,6 +124,7 @@ struct vp_model {
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 
   int basis_mode = 0;           // vp::BasisMode
+  int vertex_mode = 0;          // 0 = fan records where available, 1 = generic kernel everywhere
   // profiling
   bool profiling = false;
   float prof_ms[8] = {0};

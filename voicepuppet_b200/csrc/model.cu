@@ -59,6 +59,8 @@ void free_model(vp_model* m) {
   cudaFree(m->ltri);
   cudaFree(m->halo);
   cudaFree(m->ring);
+  cudaFree(m->fan);
+  cudaFree(m->tile_list);
   cudaFree(m->base);
   cudaFree(m->tex);
   cudaFree(m->coeff_tmp);
@@ -154,6 +156,16 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
   VP_TRY(upload(&m->ltri, m->topo.ltri));
   VP_TRY(upload(&m->halo, m->topo.halo));
   VP_TRY(upload(&m->ring, m->topo.ring));
+  VP_TRY(upload(&m->fan, m->topo.fan));
+  {
+    std::vector<int> order;
+    for (int pass = 1; pass >= 0; --pass)
+      for (int i = 0; i < m->ntiles; ++i)
+        if (m->topo.tiles[i].fan == pass) order.push_back(i);
+    m->n_fan_tiles = 0;
+    for (const vp::TileDesc& td : m->topo.tiles) m->n_fan_tiles += td.fan;
+    VP_TRY(upload(&m->tile_list, order));
+  }
 
   // per-clip state
   VP_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->base), std::max<size_t>(m->rows, 1) * sizeof(double)));
@@ -208,6 +220,16 @@ extern "C" int vp_set_basis_mode(vp_model* m, int mode) {
   m->basis_mode = mode;
   return VP_OK;
 }
+
+extern "C" int vp_set_vertex_mode(vp_model* m, int mode) {
+  VP_REQUIRE(m != nullptr, "null model");
+  VP_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (auto) or 1 (generic kernel)");
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->vertex_mode = mode;
+  return VP_OK;
+}
+
+extern "C" int vp_model_fan_tiles(const vp_model* m) { return m ? m->n_fan_tiles : -1; }
 
 extern "C" int vp_set_identity(vp_model* m, const float* id_coeff80, const float* tex_coeff80) {
   VP_REQUIRE(m != nullptr, "null model");

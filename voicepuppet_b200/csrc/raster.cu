@@ -68,7 +68,7 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
   if (ntri == 0 || nframes == 0) return VP_OK;
   static const int fpb_env = [] { const char* e = std::getenv("VPB200_SCATTER_FPB"); return e ? std::atoi(e) : 0; }();
   static const int legacy = [] { const char* e = std::getenv("VPB200_SCATTER_LEGACY"); return e ? std::atoi(e) : 0; }();
-  const int fpb = fpb_env > 0 ? fpb_env : (nframes >= 16 ? 2 : 1);  // frames per block: indices are loaded once
+  const int fpb = fpb_env > 0 ? fpb_env : (nframes >= 32 ? 4 : (nframes >= 16 ? 2 : 1));  // frames per block: indices are loaded once
   dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, (nframes + fpb - 1) / fpb);
   const bool fits32 = (unsigned long long)nframes * frame_stride < (1ull << 32) &&
                       (unsigned long long)nframes * (unsigned long long)ntri < (1ull << 32);

@@ -152,18 +152,13 @@ int launch_basis(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
 }
 
 // =========================================================================================
-// K2: one CTA per (vertex tile, group of frames).  Per frame:
-//   1. local vertex positions (own + halo) relative to the tile's first vertex, float32:
-//      (base - origin) is rounded once per tile (|.| ~ tile extent, so its float32 error is ~1e-8
-//      of the mesh scale) and the float32 expression displacement is added -> shared memory.
-//      The edges below are differences of nearby points, so this keeps their cancellation error
-//      at the level of the displacement's own float32 rounding;
-//   2. normals of the tile's triangles (cross products, float32) -> shared memory;
-//   3. per own vertex: ring sum in point_buf slot order (pad slots read a zero entry, like the
-//      zero row the reference appends), normalise, rotate, 9-band SH lighting, colour; position in
-//      float64 (base + displacement), (double) rotation, perspective projection -> one float4
-//      raster record (x, S - y, -z, rgb bytes) and/or the reference's per-vertex outputs.
-// Shared memory is double buffered across frames, so a frame costs two block barriers.
+// K2: fused vertex stage, one CTA per (vertex tile, run of frames).  Local vertex positions (own +
+// halo) are staged in shared memory per frame; the summed face normal of every own vertex comes either
+// from its FAN record (vertex_fan_kernel: 9 position gathers, any manifold mesh) or from a pass over
+// the tile's triangles plus a ring gather in point_buf slot order (vertex_tile_kernel: any point_buf);
+// finish_vertex then normalises, rotates, lights and projects.  ncu (profiles/r01d): the stage is bound by
+// the LSU data pipe (shared-memory wavefronts of the 16-byte gathers, 81 % of peak), not by HBM, which
+// is why the fan path halves the gathers instead of the bytes.
 // =========================================================================================
 struct __align__(16) FrameShared {   // per-frame constants staged in shared memory
   FrameParams par;     // 192 B: rotation (float64), translation, gamma
@@ -173,6 +168,8 @@ struct __align__(16) FrameShared {   // per-frame constants staged in shared mem
 
 struct VertexArgs {
   const TileDesc* tiles;
+  const int* tile_list;        // blockIdx.x -> tile id (this launch's slice of vp_model::tile_list)
+  const uint32_t* fan;
   const uint32_t* ltri;
   const int* halo;
   const uint16_t* ring;
@@ -223,220 +220,305 @@ __global__ void frame_prep_kernel(const FrameParams* __restrict__ params, FrameS
   }
 }
 
-// Frame loop, software pipelined over double-buffered shared memory so that a frame costs ONE block
-// barrier: iteration f computes the triangle normals of frame f (positions staged by iteration f-1),
-// stages the positions of frame f+1, synchronises, then finishes the own vertex of frame f, whose
-// shared-memory reads are independent of the next iteration's writes (the other buffers).
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_tile_kernel(const VertexArgs a) {
-  __shared__ float4 s_pos[2][kTileLV];
-  __shared__ float4 s_fn[2][kTileLT + 1];
-  __shared__ __align__(16) FrameShared s_frame[3];  // read after the barrier, restaged two iterations later
-  static_assert(sizeof(FrameParams) == 192, "FrameParams layout");
-
-  const TileDesc td = a.tiles[blockIdx.x];
-  const int tid = threadIdx.x;
-  const int nq_v = (td.nlv + kTileV - 1) / kTileV;  // CTA-uniform trip counts
-  const int nq_t = (td.nlt + kTileV - 1) / kTileV;
-
-  // ---- per-tile constants held in registers across the frame loop ------------------------
-  const double ox = __ldg(a.base + 3 * (size_t)td.v_begin), oy = __ldg(a.base + 3 * (size_t)td.v_begin + 1),
-               oz = __ldg(a.base + 3 * (size_t)td.v_begin + 2);
-  int gv[3];
-  float rx[3], ry[3], rz[3];
-  double bx = 0.0, by = 0.0, bz = 0.0;  // own vertex, float64
+// What both vertex kernels do once the summed face normal (nx, ny, nz) of the own vertex is known:
+// normalise, rotate, 9-band SH lighting, colour (float32); position, rotation(s), perspective projection
+// (float64); one float4 raster record and/or the reference's per-vertex outputs.
+__device__ __forceinline__ void finish_vertex(const VertexArgs& a, const FrameShared& fs, int f, int gv0, int orig,
+                                              float nx, float ny, float nz, float tr, float tg, float tb, double sx,
+                                              double sy, double sz) {
+  {
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);  // 0 * inf -> NaN for a vertex without faces
+    nx *= inv;
+    ny *= inv;
+    nz *= inv;
+  }
+  // rotated normal (reconstruct_mesh.py:184 / :208), lighting and colour in float32
+  const float* rf = fs.rot;
+  const float nrx = nx * rf[0] + ny * rf[3] + nz * rf[6];
+  const float nry = nx * rf[1] + ny * rf[4] + nz * rf[7];
+  const float nrz = nx * rf[2] + ny * rf[5] + nz * rf[8];
+  float lit[3];
+  {
+    const float b4 = nrx * nry, b5 = nry * nrz, b6 = 3.f * nrz * nrz - 1.f, b7 = nrx * nrz,
+                b8 = nrx * nrx - nry * nry;
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const int i = tid + q * kTileV;
-    gv[q] = td.v_begin;
-    rx[q] = ry[q] = rz[q] = 0.f;
-    if (i < td.nlv) {
-      gv[q] = (i < td.nv) ? td.v_begin + i : __ldg(a.halo + td.halo_off + i - td.nv);
-      const double x = __ldg(a.base + 3 * (size_t)gv[q]), y = __ldg(a.base + 3 * (size_t)gv[q] + 1),
-                   z = __ldg(a.base + 3 * (size_t)gv[q] + 2);
-      rx[q] = (float)(x - ox);
-      ry[q] = (float)(y - oy);
-      rz[q] = (float)(z - oz);
-      if (q == 0) {
-        bx = x;
-        by = y;
-        bz = z;
+    for (int c = 0; c < 3; ++c) {
+      const float* g = fs.sh + 9 * c;
+      lit[c] = g[0] + g[1] * nry + g[2] * nrz + g[3] * nrx + g[4] * b4 + g[5] * b5 + g[6] * b6 + g[7] * b7 + g[8] * b8;
+    }
+  }
+  const float cr = lit[0] * tr, cg = lit[1] * tg, cb = lit[2] * tb;
+
+  // geometry in float64
+  const double* R = fs.par.rot;
+  if (a.rotate_first) {  // Reconstruction_rotation rotates the shape before projecting it (:211)
+    double tx, ty, tz;
+    rotate_row(R, sx, sy, sz, tx, ty, tz);
+    sx = tx;
+    sy = ty;
+    sz = tz;
+  }
+  double px, py, zb;
+  project(R, fs.par.trans, a.focal, a.center, sx, sy, sz, px, py, zb);
+  const double pyf = a.image_size - py;  // reconstruct_mesh.py:187 / :215
+
+  if (a.vrec) {
+    // infer_bfmvid.py:93-105: (x, S - y, z_buffer) -> float32; colours clipped and truncated
+    const uint32_t rgba = clip_trunc_byte(cr) | (clip_trunc_byte(cg) << 8) | (clip_trunc_byte(cb) << 16);
+    a.vrec[(size_t)f * a.vrec_stride + gv0] =
+        make_float4((float)(px * a.raster_scale), (float)(pyf * a.raster_scale), (float)zb, __uint_as_float(rgba));
+  }
+  if (a.has_out) {
+    const size_t o = (size_t)f * a.nver + orig;
+    if (a.out.shape) {
+      a.out.shape[3 * o] = sx;
+      a.out.shape[3 * o + 1] = sy;
+      a.out.shape[3 * o + 2] = sz;
+    }
+    if (a.out.norm) {
+      a.out.norm[3 * o] = nx;
+      a.out.norm[3 * o + 1] = ny;
+      a.out.norm[3 * o + 2] = nz;
+    }
+    if (a.out.color) {
+      a.out.color[3 * o] = cr;
+      a.out.color[3 * o + 1] = cg;
+      a.out.color[3 * o + 2] = cb;
+    }
+    if (a.out.proj) {
+      a.out.proj[2 * o] = px;
+      a.out.proj[2 * o + 1] = a.out.flip_y ? pyf : py;
+    }
+    if (a.out.zbuf) a.out.zbuf[o] = zb;
+  }
+}
+
+constexpr int kSlotsV = kTileLV / kTileV;  // position-staging slots per thread (2)
+constexpr int kSlotsT = kTileLT / kTileV;  // triangle slots per thread of the generic kernel (4)
+
+// Per-thread state shared by both kernels: the thread's local vertices (own first) and how their
+// positions are staged.  Positions are float32 relative to the tile's first vertex: (base - origin) is
+// rounded once per tile (|.| ~ tile extent, so its float32 error is ~1e-8 of the mesh scale) and the float32
+// expression displacement is added; the edges the normals are made of are differences of nearby points,
+// so this keeps their cancellation error at the level of the displacement's own float32 rounding.
+struct LocalVerts {
+  int gv[kSlotsV];
+  float rx[kSlotsV], ry[kSlotsV], rz[kSlotsV];  // base - origin
+  float dx[kSlotsV], dy[kSlotsV], dz[kSlotsV];  // displacement of the frame staged next
+  double bx, by, bz;                            // own vertex, float64
+
+  __device__ __forceinline__ void load(const VertexArgs& a, const TileDesc& td, int tid) {
+    const double ox = __ldg(a.base + 3 * (size_t)td.v_begin), oy = __ldg(a.base + 3 * (size_t)td.v_begin + 1),
+                 oz = __ldg(a.base + 3 * (size_t)td.v_begin + 2);
+    bx = by = bz = 0.0;
+#pragma unroll
+    for (int q = 0; q < kSlotsV; ++q) {
+      const int i = tid + q * kTileV;
+      gv[q] = td.v_begin;
+      rx[q] = ry[q] = rz[q] = 0.f;
+      dx[q] = dy[q] = dz[q] = 0.f;
+      if (i < td.nlv) {
+        gv[q] = (i < td.nv) ? td.v_begin + i : __ldg(a.halo + td.halo_off + i - td.nv);
+        const double x = __ldg(a.base + 3 * (size_t)gv[q]), y = __ldg(a.base + 3 * (size_t)gv[q] + 1),
+                     z = __ldg(a.base + 3 * (size_t)gv[q] + 2);
+        rx[q] = (float)(x - ox);
+        ry[q] = (float)(y - oy);
+        rz[q] = (float)(z - oz);
+        if (q == 0) {
+          bx = x;
+          by = y;
+          bz = z;
+        }
       }
     }
   }
-  // triangle corners as byte offsets into a position buffer (3 x 10-bit local indices << 4 fit 3 x 14 bits:
-  // kept as the packed word, decoded with one shift-and-mask per corner)
-  uint32_t lt[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int j = tid + q * kTileV;
-    lt[q] = (j < td.nlt) ? __ldg(a.ltri + td.ltri_off + j) : 0u;
-  }
-  const bool own = tid < td.nv;
-  // ring slots as byte offsets into a normal buffer, two 16-bit halves per word; pad slots point at the
-  // zero entry kTileLT (the zero row the reference appends, reconstruct_mesh.py:47-48)
-  uint32_t ro[4] = {0, 0, 0, 0};
-  float tr = 0.f, tg = 0.f, tb = 0.f;
-  int orig = 0;
-  if (own) {
-    const uint4 rg = __ldg(reinterpret_cast<const uint4*>(a.ring) + gv[0]);
-    const uint32_t w[4] = {rg.x, rg.y, rg.z, rg.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t lo = min(w[k] & 0xFFFFu, (uint32_t)kTileLT), hi = min(w[k] >> 16, (uint32_t)kTileLT);
-      ro[k] = (lo << 4) | (hi << 20);
-    }
-    if (a.tex) {
-      tr = __ldg(a.tex + 3 * (size_t)gv[0]);
-      tg = __ldg(a.tex + 3 * (size_t)gv[0] + 1);
-      tb = __ldg(a.tex + 3 * (size_t)gv[0] + 2);
-    }
-    orig = __ldg(a.v_int2orig + gv[0]);
-  }
-  if (tid < 2) s_fn[tid][kTileLT] = make_float4(0.f, 0.f, 0.f, 0.f);  // what pad slots of the ring read
-
-  const int f_begin = blockIdx.y * a.frames_per_block;
-  const int f_end = min(a.nframes, f_begin + a.frames_per_block);
-  if (f_begin >= f_end) return;
-
-  float dx[3], dy[3], dz[3];
-#pragma unroll
-  for (int q = 0; q < 3; ++q) dx[q] = dy[q] = dz[q] = 0.f;
-  auto fetch_disp = [&](int f) {  // expression displacement of this thread's local vertices in frame f
+  __device__ __forceinline__ void fetch(const VertexArgs& a, int f, int nq_v) {  // displacement of frame f
     if (a.disp == nullptr) return;
 #pragma unroll
-    for (int q = 0; q < 3; ++q)
+    for (int q = 0; q < kSlotsV; ++q)
       if (q < nq_v) {
         const float* d = a.disp + (size_t)f * a.disp_stride + 3 * (size_t)gv[q];
         dx[q] = __ldg(d);
         dy[q] = __ldg(d + 1);
         dz[q] = __ldg(d + 2);
       }
-  };
-  auto stage = [&](int f, int buf) {  // per-frame constants and local positions of frame f -> shared memory
-    if (tid < (int)(sizeof(FrameShared) / 4))
-      reinterpret_cast<uint32_t*>(&s_frame[(f - f_begin) % 3])[tid] =
-          __ldg(reinterpret_cast<const uint32_t*>(a.fshared + f) + tid);
+  }
+  __device__ __forceinline__ void stage(float4* pos, int tid, int nq_v) const {
 #pragma unroll
-    for (int q = 0; q < 3; ++q)
-      if (q < nq_v) s_pos[buf][tid + q * kTileV] = make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
-  };
+    for (int q = 0; q < kSlotsV; ++q)
+      if (q < nq_v) pos[tid + q * kTileV] = make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
+  }
+};
 
-  // prologue: frame f_begin staged, frame f_begin + 1 in flight
-  fetch_disp(f_begin);
-  stage(f_begin, 0);
-  double own_x = bx + (double)dx[0], own_y = by + (double)dy[0], own_z = bz + (double)dz[0];
-  if (f_begin + 1 < f_end) fetch_disp(f_begin + 1);
+__device__ __forceinline__ void stage_frame_constants(const VertexArgs& a, FrameShared* dst, int f, int tid) {
+  if (tid < (int)(sizeof(FrameShared) / 4))
+    reinterpret_cast<uint32_t*>(dst)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.fshared + f) + tid);
+}
+
+// K2, fan flavour (tiles whose vertices all have fan records: any manifold mesh).  One CTA per (tile,
+// run of frames).  Per frame: the own vertex sums (u_i - v) x (u_i+1 - v) over its ring from 9 gathers of
+// staged positions, finishes (finish_vertex), stages the next frame's positions into the other buffer,
+// and the block synchronises once.  Shared memory holds positions only (no per-triangle pass).
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const VertexArgs a) {
+  __shared__ float4 s_pos[2][kTileLV];
+  __shared__ __align__(16) FrameShared s_frame[2];
+
+  const TileDesc td = a.tiles[__ldg(a.tile_list + blockIdx.x)];
+  const int tid = threadIdx.x;
+  const int nq_v = (td.nlv + kTileV - 1) / kTileV;  // CTA-uniform
+  const int f_begin = blockIdx.y * a.frames_per_block;
+  const int f_end = min(a.nframes, f_begin + a.frames_per_block);
+  if (f_begin >= f_end) return;
+
+  LocalVerts lv;
+  lv.load(a, td, tid);
+  const bool own = tid < td.nv;
+  uint32_t fan[kFanWords] = {0, 0, 0, 0, 0};
+  float tr = 0.f, tg = 0.f, tb = 0.f;
+  if (own) {
+#pragma unroll
+    for (int k = 0; k < kFanWords; ++k) fan[k] = __ldg(a.fan + (size_t)lv.gv[0] * kFanWords + k);
+    if (a.tex) {
+      tr = __ldg(a.tex + 3 * (size_t)lv.gv[0]);
+      tg = __ldg(a.tex + 3 * (size_t)lv.gv[0] + 1);
+      tb = __ldg(a.tex + 3 * (size_t)lv.gv[0] + 2);
+    }
+  }
+
+  // prologue: frame f_begin staged, displacement of frame f_begin + 1 in flight
+  lv.fetch(a, f_begin, nq_v);
+  stage_frame_constants(a, &s_frame[0], f_begin, tid);
+  lv.stage(s_pos[0], tid, nq_v);
+  float d0x = lv.dx[0], d0y = lv.dy[0], d0z = lv.dz[0];  // own displacement of the frame being finished
+  if (f_begin + 1 < f_end) lv.fetch(a, f_begin + 1, nq_v);
   __syncthreads();
 
   for (int f = f_begin; f < f_end; ++f) {
     const int buf = (f - f_begin) & 1;
-    // ---- triangle normals of frame f (reconstruct_mesh.py:41-46) ---------------------------
-    {
+    if (own) {
       const char* pos = reinterpret_cast<const char*>(s_pos[buf]);
+      const float4 pv = s_pos[buf][tid];
+      float nx = 0.f, ny = 0.f, nz = 0.f;
+      float4 p = *reinterpret_cast<const float4*>(pos + (fan[0] & 0xFFFFu));
+      float ex = p.x - pv.x, ey = p.y - pv.y, ez = p.z - pv.z;
+      const uint32_t mask = fan[4] >> 16;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < nq_t) {
-          const float4 p1 = *reinterpret_cast<const float4*>(pos + ((lt[q] << 4) & 0x3FF0u)),
-                       p2 = *reinterpret_cast<const float4*>(pos + ((lt[q] >> 6) & 0x3FF0u)),
-                       p3 = *reinterpret_cast<const float4*>(pos + ((lt[q] >> 16) & 0x3FF0u));
-          const float e1x = p1.x - p2.x, e1y = p1.y - p2.y, e1z = p1.z - p2.z;
-          const float e2x = p2.x - p3.x, e2y = p2.y - p3.y, e2z = p2.z - p3.z;
-          s_fn[buf][tid + q * kTileV] =
-              make_float4(e1y * e2z - e1z * e2y, e1z * e2x - e1x * e2z, e1x * e2y - e1y * e2x, 0.f);
+      for (int i = 0; i < kFanEntries - 1; ++i) {
+        const uint32_t off = ((i + 1) & 1) ? (fan[(i + 1) >> 1] >> 16) : (fan[(i + 1) >> 1] & 0xFFFFu);
+        p = *reinterpret_cast<const float4*>(pos + off);
+        const float gx = p.x - pv.x, gy = p.y - pv.y, gz = p.z - pv.z;
+        if (mask & (1u << i)) {
+          nx += ey * gz - ez * gy;
+          ny += ez * gx - ex * gz;
+          nz += ex * gy - ey * gx;
         }
+        ex = gx;
+        ey = gy;
+        ez = gz;
+      }
+      int orig = 0;
+      if (a.has_out) orig = __ldg(a.v_int2orig + lv.gv[0]);
+      finish_vertex(a, s_frame[buf], f, lv.gv[0], orig, nx, ny, nz, tr, tg, tb, lv.bx + (double)d0x,
+                    lv.by + (double)d0y, lv.bz + (double)d0z);
     }
-    // ---- stage frame f + 1 (other buffers), fetch frame f + 2 --------------------------------
-    const double cur_x = own_x, cur_y = own_y, cur_z = own_z;
+    // ---- stage frame f + 1 into the other buffers (their readers passed the previous barrier) ----
     if (f + 1 < f_end) {
-      stage(f + 1, buf ^ 1);
-      own_x = bx + (double)dx[0];
-      own_y = by + (double)dy[0];
-      own_z = bz + (double)dz[0];
-      if (f + 2 < f_end) fetch_disp(f + 2);
+      stage_frame_constants(a, &s_frame[buf ^ 1], f + 1, tid);
+      lv.stage(s_pos[buf ^ 1], tid, nq_v);
+      d0x = lv.dx[0];
+      d0y = lv.dy[0];
+      d0z = lv.dz[0];
+      if (f + 2 < f_end) lv.fetch(a, f + 2, nq_v);
     }
     __syncthreads();
-    if (!own) continue;
-    // ---- the own vertex of frame f -----------------------------------------------------------
-    const FrameShared& fs = s_frame[(f - f_begin) % 3];
-    float nx = 0.f, ny = 0.f, nz = 0.f;
-    {
-      const char* fnb = reinterpret_cast<const char*>(s_fn[buf]);
+  }
+}
+
+// K2, generic flavour (tiles where point_buf does not chain into fans: non-manifold meshes, faces listed
+// for vertices they do not contain).  Per frame: triangle normals of the tile -> shared memory, block
+// barrier, then per own vertex the ring sum in point_buf slot order (pad slots read a zero entry, like the
+// zero row the reference appends), finish_vertex, stage the next frame, block barrier.
+__global__ void __launch_bounds__(kTileV, 5) vertex_tile_kernel(const VertexArgs a) {
+  __shared__ float4 s_pos[2][kTileLV];
+  __shared__ float4 s_fn[kTileLT + 1];
+  __shared__ __align__(16) FrameShared s_frame[2];
+  static_assert(sizeof(FrameParams) == 192, "FrameParams layout");
+
+  const TileDesc td = a.tiles[__ldg(a.tile_list + blockIdx.x)];
+  const int tid = threadIdx.x;
+  const int nq_v = (td.nlv + kTileV - 1) / kTileV;  // CTA-uniform trip counts
+  const int nq_t = (td.nlt + kTileV - 1) / kTileV;
+  const int f_begin = blockIdx.y * a.frames_per_block;
+  const int f_end = min(a.nframes, f_begin + a.frames_per_block);
+  if (f_begin >= f_end) return;
+
+  LocalVerts lv;
+  lv.load(a, td, tid);
+  uint32_t lt[kSlotsT];
+#pragma unroll
+  for (int q = 0; q < kSlotsT; ++q) {
+    const int j = tid + q * kTileV;
+    lt[q] = (j < td.nlt) ? __ldg(a.ltri + td.ltri_off + j) : 0u;
+  }
+  const bool own = tid < td.nv;
+  uint4 rg = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+  float tr = 0.f, tg = 0.f, tb = 0.f;
+  if (own) {
+    rg = __ldg(reinterpret_cast<const uint4*>(a.ring) + lv.gv[0]);
+    if (a.tex) {
+      tr = __ldg(a.tex + 3 * (size_t)lv.gv[0]);
+      tg = __ldg(a.tex + 3 * (size_t)lv.gv[0] + 1);
+      tb = __ldg(a.tex + 3 * (size_t)lv.gv[0] + 2);
+    }
+  }
+  if (tid == 0) s_fn[kTileLT] = make_float4(0.f, 0.f, 0.f, 0.f);  // what pad slots of the ring read
+
+  lv.fetch(a, f_begin, nq_v);
+  stage_frame_constants(a, &s_frame[0], f_begin, tid);
+  lv.stage(s_pos[0], tid, nq_v);
+  float d0x = lv.dx[0], d0y = lv.dy[0], d0z = lv.dz[0];
+  if (f_begin + 1 < f_end) lv.fetch(a, f_begin + 1, nq_v);
+  __syncthreads();
+
+  for (int f = f_begin; f < f_end; ++f) {
+    const int buf = (f - f_begin) & 1;
+    // ---- triangle normals (reconstruct_mesh.py:41-46) --------------------------------------
+#pragma unroll
+    for (int q = 0; q < kSlotsT; ++q)
+      if (q < nq_t) {
+        const float4 p1 = s_pos[buf][lt[q] & 1023u], p2 = s_pos[buf][(lt[q] >> 10) & 1023u],
+                     p3 = s_pos[buf][(lt[q] >> 20) & 1023u];
+        const float e1x = p1.x - p2.x, e1y = p1.y - p2.y, e1z = p1.z - p2.z;
+        const float e2x = p2.x - p3.x, e2y = p2.y - p3.y, e2z = p2.z - p3.z;
+        s_fn[tid + q * kTileV] = make_float4(e1y * e2z - e1z * e2y, e1z * e2x - e1x * e2z, e1x * e2y - e1y * e2x, 0.f);
+      }
+    __syncthreads();
+    if (own) {
+      float nx = 0.f, ny = 0.f, nz = 0.f;
+      const uint32_t w[4] = {rg.x, rg.y, rg.z, rg.w};
 #pragma unroll
       for (int s = 0; s < VP_RING; ++s) {
-        const uint32_t off = (s & 1) ? (ro[s >> 1] >> 16) : (ro[s >> 1] & 0xFFFFu);
-        const float4 fn = *reinterpret_cast<const float4*>(fnb + off);
+        const uint32_t j = min((w[s >> 1] >> ((s & 1) * 16)) & 0xFFFFu, (uint32_t)kTileLT);
+        const float4 fn = s_fn[j];
         nx += fn.x;
         ny += fn.y;
         nz += fn.z;
       }
+      int orig = 0;
+      if (a.has_out) orig = __ldg(a.v_int2orig + lv.gv[0]);
+      finish_vertex(a, s_frame[buf], f, lv.gv[0], orig, nx, ny, nz, tr, tg, tb, lv.bx + (double)d0x,
+                    lv.by + (double)d0y, lv.bz + (double)d0z);
     }
-    {
-      const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);  // 0 * inf -> NaN for a vertex without faces
-      nx *= inv;
-      ny *= inv;
-      nz *= inv;
+    if (f + 1 < f_end) {
+      stage_frame_constants(a, &s_frame[buf ^ 1], f + 1, tid);
+      lv.stage(s_pos[buf ^ 1], tid, nq_v);
+      d0x = lv.dx[0];
+      d0y = lv.dy[0];
+      d0z = lv.dz[0];
+      if (f + 2 < f_end) lv.fetch(a, f + 2, nq_v);
     }
-    // rotated normal (reconstruct_mesh.py:184 / :208), lighting and colour in float32
-    const float* rf = fs.rot;
-    const float nrx = nx * rf[0] + ny * rf[3] + nz * rf[6];
-    const float nry = nx * rf[1] + ny * rf[4] + nz * rf[7];
-    const float nrz = nx * rf[2] + ny * rf[5] + nz * rf[8];
-    float lit[3];
-    {
-      const float b4 = nrx * nry, b5 = nry * nrz, b6 = 3.f * nrz * nrz - 1.f, b7 = nrx * nrz,
-                  b8 = nrx * nrx - nry * nry;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* g = fs.sh + 9 * c;
-        lit[c] = g[0] + g[1] * nry + g[2] * nrz + g[3] * nrx + g[4] * b4 + g[5] * b5 + g[6] * b6 + g[7] * b7 + g[8] * b8;
-      }
-    }
-    const float cr = lit[0] * tr, cg = lit[1] * tg, cb = lit[2] * tb;
-
-    // geometry in float64
-    const double* R = fs.par.rot;
-    double sx = cur_x, sy = cur_y, sz = cur_z;
-    if (a.rotate_first) {  // Reconstruction_rotation rotates the shape before projecting it (:211)
-      double tx, ty, tz;
-      rotate_row(R, sx, sy, sz, tx, ty, tz);
-      sx = tx;
-      sy = ty;
-      sz = tz;
-    }
-    double px, py, zb;
-    project(R, fs.par.trans, a.focal, a.center, sx, sy, sz, px, py, zb);
-    const double pyf = a.image_size - py;  // reconstruct_mesh.py:187 / :215
-
-    if (a.vrec) {
-      // infer_bfmvid.py:93-105: (x, S - y, z_buffer) -> float32; colours clipped and truncated
-      const uint32_t rgba = clip_trunc_byte(cr) | (clip_trunc_byte(cg) << 8) | (clip_trunc_byte(cb) << 16);
-      a.vrec[(size_t)f * a.vrec_stride + gv[0]] =
-          make_float4((float)(px * a.raster_scale), (float)(pyf * a.raster_scale), (float)zb, __uint_as_float(rgba));
-    }
-    if (a.has_out) {
-      const size_t o = (size_t)f * a.nver + orig;
-      if (a.out.shape) {
-        a.out.shape[3 * o] = sx;
-        a.out.shape[3 * o + 1] = sy;
-        a.out.shape[3 * o + 2] = sz;
-      }
-      if (a.out.norm) {
-        a.out.norm[3 * o] = nx;
-        a.out.norm[3 * o + 1] = ny;
-        a.out.norm[3 * o + 2] = nz;
-      }
-      if (a.out.color) {
-        a.out.color[3 * o] = cr;
-        a.out.color[3 * o + 1] = cg;
-        a.out.color[3 * o + 2] = cb;
-      }
-      if (a.out.proj) {
-        a.out.proj[2 * o] = px;
-        a.out.proj[2 * o + 1] = a.out.flip_y ? pyf : py;
-      }
-      if (a.out.zbuf) a.out.zbuf[o] = zb;
-    }
+    __syncthreads();
   }
 }
 
@@ -446,6 +528,8 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   if (nframes == 0 || m->ntiles == 0) return VP_OK;
   VertexArgs a;
   a.tiles = m->tiles;
+  a.tile_list = m->tile_list;
+  a.fan = m->fan;
   a.ltri = m->ltri;
   a.halo = m->halo;
   a.ring = m->ring;
@@ -460,13 +544,6 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   VP_LAUNCH_CHECK();
   a.fshared = fshared;
   a.nframes = nframes;
-  static const int fpb_env = [] { const char* e = std::getenv("VPB200_VERTEX_FPB"); return e ? std::atoi(e) : 0; }();
-  // One resident wave: the tile constants (dependent global loads) and the pipeline prologue are paid
-  // once per CTA, so each CTA takes as many frames as keeps the grid within the 6 CTAs/SM that fit.
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-  const int groups = std::max(1, std::min(nframes, (sms * 6) / std::max(m->ntiles, 1)));
-  a.frames_per_block = fpb_env > 0 ? fpb_env : (nframes + groups - 1) / groups;
   a.rotate_first = rotate_first;
   a.has_out = (out.shape || out.norm || out.color || out.proj || out.zbuf) ? 1 : 0;
   a.focal = focal;
@@ -477,15 +554,38 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.vrec_stride = (size_t)m->vrec_stride;
   a.out = out;
   a.nver = m->nver;
-  dim3 grid(m->ntiles, (nframes + a.frames_per_block - 1) / a.frames_per_block);
+  static const int fpb_env = [] { const char* e = std::getenv("VPB200_VERTEX_FPB"); return e ? std::atoi(e) : 0; }();
   static const int minb_env = [] { const char* e = std::getenv("VPB200_VERTEX_MINB"); return e ? std::atoi(e) : 0; }();
-  if (minb_env == 5)
-    vertex_tile_kernel<5><<<grid, kTileV, 0, st>>>(a);
-  else if (minb_env == 7)
-    vertex_tile_kernel<7><<<grid, kTileV, 0, st>>>(a);
-  else
-    vertex_tile_kernel<6><<<grid, kTileV, 0, st>>>(a);
-  VP_LAUNCH_CHECK();
+  static const int force_generic = [] { const char* e = std::getenv("VPB200_VERTEX_GENERIC"); return e ? std::atoi(e) : 0; }();
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  // Frames per CTA: the tile constants (dependent global loads) and the pipeline prologue are paid once per
+  // CTA, so a CTA takes a run of frames; runs are sized for about `waves` resident waves of CTAs.
+  auto frames_per_block = [&](int ntiles, int blocks_per_sm, int waves) {
+    if (fpb_env > 0) return fpb_env;
+    const int groups = std::max(1, std::min(nframes, (sms * blocks_per_sm * waves) / std::max(ntiles, 1)));
+    return (nframes + groups - 1) / groups;
+  };
+  const int n_fan = (force_generic || m->vertex_mode == 1) ? 0 : m->n_fan_tiles;
+  if (n_fan > 0) {
+    const int minb = minb_env > 0 ? minb_env : 8;
+    a.frames_per_block = frames_per_block(n_fan, minb, 2);
+    dim3 grid(n_fan, (nframes + a.frames_per_block - 1) / a.frames_per_block);
+    if (minb <= 6)
+      vertex_fan_kernel<6><<<grid, kTileV, 0, st>>>(a);
+    else if (minb == 7)
+      vertex_fan_kernel<7><<<grid, kTileV, 0, st>>>(a);
+    else
+      vertex_fan_kernel<8><<<grid, kTileV, 0, st>>>(a);
+    VP_LAUNCH_CHECK();
+  }
+  if (m->ntiles - n_fan > 0) {
+    a.tile_list = m->tile_list + n_fan;
+    a.frames_per_block = frames_per_block(m->ntiles - n_fan, 5, 2);
+    dim3 grid(m->ntiles - n_fan, (nframes + a.frames_per_block - 1) / a.frames_per_block);
+    vertex_tile_kernel<<<grid, kTileV, 0, st>>>(a);
+    VP_LAUNCH_CHECK();
+  }
   return VP_OK;
 }
 

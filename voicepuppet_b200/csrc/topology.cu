@@ -10,7 +10,10 @@
 //     exceed 128 own vertices, kTileLV local vertices or kTileLT local triangles;
 //   * point_buf slot order is preserved (the reference sums the ring in column order);
 //   * triangles are renumbered by their smallest renumbered vertex for the rasterizer, and
-//     keep their ORIGINAL index for the z-buffer tie-break.
+//     keep their ORIGINAL index for the z-buffer tie-break;
+//   * where every face a vertex's point_buf row lists really contains the vertex and the faces chain
+//     into at most 9 ring vertices (any manifold mesh: closed or open fans up to valence 8), the tile
+//     also gets FAN records (launch.h), which let the vertex kernel skip the per-triangle pass.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -92,6 +95,7 @@ int build_topology(Topology& out, int nver, int ntri, const int* tri, const int*
 
   // ---- vertex tiles ----------------------------------------------------------------------
   out.ring.assign((size_t)nver * VP_RING, kRingPad);
+  out.fan.assign((size_t)nver * kFanWords, 0u);
   std::vector<int> tri_stamp(ntri, -1), tri_local(ntri, 0);   // tile id that last saw the triangle
   std::vector<int> ver_stamp(nver, -1), ver_local(nver, 0);   // ... the (internal) vertex
   std::vector<int> cur_tris, cur_touched;                     // in first-seen order
@@ -156,6 +160,64 @@ int build_topology(Topology& out, int nver, int ntri, const int* tri, const int*
     }
     td.nlv = next;
     td.nlt = (int)cur_tris.size();
+    // ---- fan records ---------------------------------------------------------------------
+    td.fan = 1;
+    for (int iv = td.v_begin; iv < td.v_begin + td.nv && td.fan; ++iv) {
+      const int ov = out.v_int2orig[iv];
+      int fp[VP_RING], fq[VP_RING], nf = 0;  // the other two corners (tile-local) of every listed face
+      for (int s = 0; s < VP_RING && td.fan; ++s) {
+        const int f = point_buf[(size_t)ov * VP_RING + s];
+        if (f < 0 || f >= ntri) continue;
+        int k = -1;
+        for (int c = 2; c >= 0; --c)
+          if (tri[3 * (size_t)f + c] == ov) k = c;
+        if (k < 0) {  // point_buf names a face that does not contain the vertex: generic path
+          td.fan = 0;
+          break;
+        }
+        fp[nf] = ver_local[out.v_orig2int[tri[3 * (size_t)f + (k + 1) % 3]]];
+        fq[nf] = ver_local[out.v_orig2int[tri[3 * (size_t)f + (k + 2) % 3]]];
+        ++nf;
+      }
+      if (!td.fan) break;
+      int entries[2 * VP_RING + 2], ne = 0;
+      uint32_t mask = 0;
+      bool used[VP_RING] = {false, false, false, false, false, false, false, false};
+      for (int done = 0; done < nf && ne <= kFanEntries;) {
+        int start = -1;  // a face no other unused face leads into, else the first unused one
+        for (int i = 0; i < nf && start < 0; ++i) {
+          if (used[i]) continue;
+          bool led = false;
+          for (int j = 0; j < nf; ++j) led |= (!used[j] && j != i && fq[j] == fp[i]);
+          if (!led) start = i;
+        }
+        for (int i = 0; i < nf && start < 0; ++i)
+          if (!used[i]) start = i;
+        entries[ne++] = fp[start];
+        for (int cur = start; cur >= 0 && ne <= kFanEntries;) {
+          mask |= 1u << (ne - 1);
+          entries[ne++] = fq[cur];
+          used[cur] = true;
+          ++done;
+          int nxt = -1;
+          for (int j = 0; j < nf && nxt < 0; ++j)
+            if (!used[j] && fp[j] == fq[cur]) nxt = j;
+          cur = nxt;
+        }
+      }
+      if (ne > kFanEntries) {
+        td.fan = 0;
+        break;
+      }
+      const int self = iv - td.v_begin;
+      while (ne < kFanEntries) entries[ne++] = self;
+      uint32_t* w = &out.fan[(size_t)iv * kFanWords];
+      for (int k = 0; k < 4; ++k) w[k] = ((uint32_t)entries[2 * k] << 4) | ((uint32_t)entries[2 * k + 1] << 20);
+      w[4] = ((uint32_t)entries[8] << 4) | (mask << 16);
+    }
+    if (!td.fan)
+      for (int iv = td.v_begin; iv < td.v_begin + td.nv; ++iv)
+        for (int k = 0; k < kFanWords; ++k) out.fan[(size_t)iv * kFanWords + k] = 0;
     td.ltri_off = (int)out.ltri.size();
     for (int f : cur_tris) {
       const uint32_t a = (uint32_t)ver_local[out.v_orig2int[tri[3 * (size_t)f]]];
@@ -200,7 +262,7 @@ extern "C" int vp_topology_sizes(const vp_topology* h, int* ntiles, int* nltri, 
 }
 
 extern "C" int vp_topology_copy(const vp_topology* h, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
-                                int* halo, uint16_t* ring) {
+                                int* halo, uint16_t* ring, uint32_t* fan) {
   VP_REQUIRE(h != nullptr, "null handle");
   const vp::Topology& t = h->t;
   if (v_int2orig) std::memcpy(v_int2orig, t.v_int2orig.data(), t.v_int2orig.size() * sizeof(int));
@@ -209,5 +271,6 @@ extern "C" int vp_topology_copy(const vp_topology* h, int* v_int2orig, int* tri_
   if (ltri) std::memcpy(ltri, t.ltri.data(), t.ltri.size() * sizeof(uint32_t));
   if (halo) std::memcpy(halo, t.halo.data(), t.halo.size() * sizeof(int));
   if (ring) std::memcpy(ring, t.ring.data(), t.ring.size() * sizeof(uint16_t));
+  if (fan) std::memcpy(fan, t.fan.data(), t.fan.size() * sizeof(uint32_t));
   return VP_OK;
 }

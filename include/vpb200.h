@@ -98,6 +98,24 @@ int vp_rasterize_triangles_core(const float* vertices, const int* triangles, flo
                                 int* triangle_buffer, float* barycentric_weight,
                                 int nver, int ntri, int h, int w);
 
+/* render_texture_core (mesh_core_cython.pyx:80-99 -> mesh_core.cpp:234-333): z-buffer decision of
+ * rasterize_triangles_core, the winner's texel sampled nearest (mapping_type 0) or bilinearly.
+ * image[h*w*c] f32 (written only where a triangle wins), vertices[nver*3], triangles[ntri*3],
+ * texture[tex_h*tex_w*tex_c] f32, tex_coords[tex_nver*3] (x, y, unused), tex_triangles[ntri*3],
+ * depth_buffer[h*w].  Reference quirk kept: the texture y coordinate is read with the MESH vertex index
+ * (mesh_core.cpp:270-272), so tex_coords needs a row for every mesh index used.  Unlike the reference,
+ * out-of-range indices are an error (VP_ERR_ARG) instead of an out-of-bounds read. */
+int vp_render_texture_core(float* image, const float* vertices, const int* triangles, const float* texture,
+                           const float* tex_coords, const int* tex_triangles, float* depth_buffer,
+                           int nver, int tex_nver, int ntri, int h, int w, int c,
+                           int tex_h, int tex_w, int tex_c, int mapping_type);
+
+/* get_normal_core (mesh_core_cython.pyx:40-47 -> mesh_core.cpp:85-105): normal[v] += tri_normal[i] for the
+ * three corners of every triangle i, accumulated in ascending triangle order in float32 -- reproduced
+ * bit-exactly by an ordered per-vertex gather.  normal[nver*3] in/out, tri_normal[ntri*3],
+ * triangles[ntri*3].  `nver` is new (the reference trusts the indices). */
+int vp_get_normal_core(float* normal, const float* tri_normal, const int* triangles, int nver, int ntri);
+
 /* Batched device-pointer form of render_colors_core: `nframes` meshes sharing one triangle
  * list.  vertices[nframes][3*nver], colors[nframes][c*nver], image[nframes][h*w*c],
  * face_mask[nframes][h*w], depth_buffer[nframes][h*w], triangle_id (NULL ok)[nframes][h*w]. */

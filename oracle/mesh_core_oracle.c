@@ -258,3 +258,110 @@ int vpo_render_colors_near_ties(const float* vertices, const int* triangles, int
   free(second);
   return count;
 }
+
+/*
+ * render_texture, order independent: _render_texture_core, mesh_core.cpp:234-333.
+ * The z-buffer decision is rasterize_triangles' (border rule :290, interpolated depth :293, strict '>'
+ * :295), so the winner per pixel is found the same way; the winner's texel is then recomputed with the
+ * reference's float32 expressions:
+ *   tex_p = tex_p0*w0 + tex_p1*w1 + tex_p2*w2  (point::operator*, operator+, mesh_core.h:32-46; left to right)
+ *   clamp to [0, tex_w-1] x [0, tex_h-1] with std::min / std::max (:302-303)
+ *   nearest: texture[round(y)][round(x)] (:311); bilinear: ul*(1-xd)*(1-yd) + ur*xd*(1-yd) + dl*(1-xd)*yd +
+ *   dr*xd*yd, left to right (:315-320).
+ * Reference quirk kept: the texture y coordinate is read with the MESH vertex index, stride 3 (:270-272).
+ * The image is written only where a triangle wins; elsewhere the caller's values stay.
+ */
+int vpo_render_texture(float* image, const float* vertices, const int* triangles, const float* texture,
+                       const float* tex_coords, const int* tex_triangles, float* depth_buffer,
+                       int nver, int tex_nver, int ntri, int h, int w, int c, int tex_h, int tex_w, int tex_c,
+                       int mapping_type, int reverse) {
+  size_t npix = (size_t)h * (size_t)w, p;
+  uint64_t* keys = keys_from_depth(depth_buffer, npix);
+  int n, x, y, k;
+  (void)nver; (void)tex_nver;
+  if (!keys) return -1;
+  for (n = 0; n < ntri; n++) {
+    int i = reverse ? (ntri - 1 - n) : n;
+    tri_setup s;
+    setup_triangle(&s, vertices, triangles + 3 * (size_t)i, h, w);
+    if (!s.live) continue;
+    for (y = s.y_lo; y <= s.y_hi; y++)
+      for (x = s.x_lo; x <= s.x_hi; x++) {
+        float u, v, wgt[3];
+        float fx = (float)x, fy = (float)y;
+        pixel_uv(&s, x, y, &u, &v);
+        if (fx < 2 || fx > w - 3 || fy < 2 || fy > h - 3 || uv_inside(u, v))
+          offer(keys, (size_t)y * w + x, weights_and_depth(&s, u, v, wgt), i);
+      }
+  }
+  for (p = 0; p < npix; p++) {
+    int i = key_winner(keys[p]);
+    if (i < 0) continue;
+    {
+      const int* t = triangles + 3 * (size_t)i;
+      const int* tt = tex_triangles + 3 * (size_t)i;
+      tri_setup s;
+      float u, v, wgt[3], tx, ty, xd, yd;
+      setup_triangle(&s, vertices, t, h, w);
+      pixel_uv(&s, (int)(p % (size_t)w), (int)(p / (size_t)w), &u, &v);
+      depth_buffer[p] = weights_and_depth(&s, u, v, wgt);
+      /* x from the texture triangle's vertex, y from the MESH triangle's vertex (:270-272) */
+      tx = (wgt[0] * tex_coords[3 * (size_t)tt[0]] + wgt[1] * tex_coords[3 * (size_t)tt[1]]) +
+           wgt[2] * tex_coords[3 * (size_t)tt[2]];
+      ty = (wgt[0] * tex_coords[3 * (size_t)t[0] + 1] + wgt[1] * tex_coords[3 * (size_t)t[1] + 1]) +
+           wgt[2] * tex_coords[3 * (size_t)t[2] + 1];
+      tx = hi2(lo2(tx, (float)(tex_w - 1)), 0.0f);
+      ty = hi2(lo2(ty, (float)(tex_h - 1)), 0.0f);
+      yd = ty - floorf(ty);
+      xd = tx - floorf(tx);
+      for (k = 0; k < c; k++) {
+        if (mapping_type == 0) {
+          image[p * c + k] = texture[(size_t)trunc_x86(roundf(ty)) * tex_w * tex_c + (size_t)trunc_x86(roundf(tx)) * tex_c + k];
+        } else {
+          size_t y0 = (size_t)trunc_x86(floorf(ty)), y1 = (size_t)trunc_x86(ceilf(ty));
+          size_t x0 = (size_t)trunc_x86(floorf(tx)), x1 = (size_t)trunc_x86(ceilf(tx));
+          float ul = texture[y0 * tex_w * tex_c + x0 * tex_c + k];
+          float ur = texture[y0 * tex_w * tex_c + x1 * tex_c + k];
+          float dl = texture[y1 * tex_w * tex_c + x0 * tex_c + k];
+          float dr = texture[y1 * tex_w * tex_c + x1 * tex_c + k];
+          image[p * c + k] = ((ul * (1 - xd) * (1 - yd) + ur * xd * (1 - yd)) + dl * (1 - xd) * yd) + dr * xd * yd;
+        }
+      }
+    }
+  }
+  free(keys);
+  return 0;
+}
+
+/*
+ * get_normal, gather form: _get_normal_core, mesh_core.cpp:85-105 adds tri_normal[i] to the three corner
+ * vertices of triangle i, walking i upwards; per vertex that is a left-to-right float32 sum over its
+ * (triangle, corner) incidences in ascending order, starting from the caller's value.  The restatement
+ * builds the incidence lists with a stable counting sort and sums each vertex on its own (what the GPU does).
+ * Returns -1 on allocation failure, -2 when a triangle names a vertex outside [0, nver).
+ */
+int vpo_get_normal(float* normal, const float* tri_normal, const int* triangles, int nver, int ntri) {
+  size_t ninc = 3 * (size_t)ntri, q;
+  int* start = (int*)calloc((size_t)nver + 1, sizeof(int));
+  int* fill;
+  int* inc;
+  int v;
+  if (!start) return -1;
+  for (q = 0; q < ninc; q++) {
+    if (triangles[q] < 0 || triangles[q] >= nver) { free(start); return -2; }
+    start[triangles[q] + 1]++;
+  }
+  for (v = 0; v < nver; v++) start[v + 1] += start[v];
+  fill = (int*)malloc(((size_t)nver + 1) * sizeof(int));
+  inc = (int*)malloc((ninc ? ninc : 1) * sizeof(int));
+  if (!fill || !inc) { free(start); free(fill); free(inc); return -1; }
+  memcpy(fill, start, ((size_t)nver + 1) * sizeof(int));
+  for (q = 0; q < ninc; q++) inc[fill[triangles[q]]++] = (int)(q / 3);   /* stable: ascending (triangle, corner) */
+  for (v = 0; v < nver; v++) {
+    int j, k;
+    for (j = start[v]; j < start[v + 1]; j++)
+      for (k = 0; k < 3; k++) normal[3 * (size_t)v + k] = normal[3 * (size_t)v + k] + tri_normal[3 * (size_t)inc[j] + k];
+  }
+  free(start); free(fill); free(inc);
+  return 0;
+}

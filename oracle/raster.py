@@ -42,6 +42,10 @@ class Oracle(object):
       lib.vpo_rasterize_triangles.restype = ctypes.c_int
       lib.vpo_render_colors_near_ties.argtypes = [_f32p, _i32p] + [ctypes.c_int] * 4 + [_u8p]
       lib.vpo_render_colors_near_ties.restype = ctypes.c_int
+      lib.vpo_render_texture.argtypes = [_f32p, _f32p, _i32p, _f32p, _f32p, _i32p, _f32p] + [ctypes.c_int] * 11
+      lib.vpo_render_texture.restype = ctypes.c_int
+      lib.vpo_get_normal.argtypes = [_f32p, _f32p, _i32p, ctypes.c_int, ctypes.c_int]
+      lib.vpo_get_normal.restype = ctypes.c_int
       cls._lib = lib
     return cls._lib
 
@@ -63,6 +67,23 @@ class Oracle(object):
         _p(_chk(vertices, np.float32), _f32p), _p(_chk(triangles, np.int32), _i32p),
         _p(_chk(depth_buffer, np.float32), _f32p), _p(_chk(triangle_buffer, np.int32), _i32p),
         _p(_chk(barycentric_weight, np.float32), _f32p), nver, ntri, h, w, int(reverse))
+    assert rc == 0
+
+  @classmethod
+  def render_texture(cls, image, vertices, triangles, texture, tex_coords, tex_triangles, depth_buffer,
+                     nver, tex_nver, ntri, h, w, c, tex_h, tex_w, tex_c, mapping_type, reverse=False):
+    rc = cls.lib().vpo_render_texture(
+        _p(_chk(image, np.float32), _f32p), _p(_chk(vertices, np.float32), _f32p),
+        _p(_chk(triangles, np.int32), _i32p), _p(_chk(texture, np.float32), _f32p),
+        _p(_chk(tex_coords, np.float32), _f32p), _p(_chk(tex_triangles, np.int32), _i32p),
+        _p(_chk(depth_buffer, np.float32), _f32p),
+        nver, tex_nver, ntri, h, w, c, tex_h, tex_w, tex_c, mapping_type, int(reverse))
+    assert rc == 0
+
+  @classmethod
+  def get_normal(cls, normal, tri_normal, triangles, ntri):
+    rc = cls.lib().vpo_get_normal(_p(_chk(normal, np.float32), _f32p), _p(_chk(tri_normal, np.float32), _f32p),
+                                  _p(_chk(triangles, np.int32), _i32p), normal.size // 3, ntri)
     assert rc == 0
 
   @classmethod

@@ -65,6 +65,8 @@ SIGNATURES = {
     'vp_peer_wait': (_i, [_vp, _i, ctypes.c_uint, _vp]),
     'vp_render_colors_core': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
     'vp_rasterize_triangles_core': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    'vp_render_texture_core': (_i, [_vp] * 7 + [_i] * 10),
+    'vp_get_normal_core': (_i, [_vp, _vp, _vp, _i, _i]),
     'vp_render_colors_batch_dev': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'vp_model_create': (_i, [ctypes.POINTER(_vp), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     'vp_model_destroy': (None, [_vp]),

@@ -226,3 +226,5 @@ extern "C" int vp_rasterize_triangles_core(const float* vertices, const int* tri
   VP_CUDA(cudaStreamSynchronize(st));
   return VP_OK;
 }
+
+#include "mesh_extra.cuh"

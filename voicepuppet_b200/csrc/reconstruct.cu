@@ -6,6 +6,7 @@
 // :172-223 (Reconstruction / Reconstruction_rotation).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "launch.h"
@@ -17,27 +18,46 @@ namespace vp {
 // K0: out[r] = mean[r] + sum_k basis[r][k] * coeff[k]  (- center[r % 3]), float64 accumulate.
 // Runs once per clip ("identity mean precomputed once").
 // =========================================================================================
+// Four lanes share a basis row and read it as 16-byte vectors (lane l takes vectors l, l + 4, ...), so a
+// warp streams 8 consecutive rows as one contiguous, fully coalesced span; float64 accumulation, two
+// shuffles to combine the four partial sums.
 template <typename B, typename O, int K>
 __global__ void __launch_bounds__(256)
 identity_kernel(const B* __restrict__ basis, const double* __restrict__ mean, const float* __restrict__ coeff,
                 double c0, double c1, double c2, O* __restrict__ out, int rows) {
+  constexpr int kVec = 16 / sizeof(B);       // elements per 16-byte vector
+  constexpr int kVecsPerRow = K / kVec;      // 20 (float) or 40 (double)
+  static_assert(K % (4 * kVec) == 0, "row must split into 16-byte vectors over four lanes");
   __shared__ double cs[K];
   if (threadIdx.x < K) cs[threadIdx.x] = (double)coeff[threadIdx.x];
   __syncthreads();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const B* row = basis + (size_t)r * K;
+  const int sub = threadIdx.x & 3;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   double acc = 0.0;
-#pragma unroll 8
-  for (int k = 0; k < K; ++k) acc += (double)__ldg(row + k) * cs[k];
-  acc += mean[r];
-  const int axis = r % 3;
-  acc -= (axis == 0) ? c0 : (axis == 1 ? c1 : c2);
-  out[r] = static_cast<O>(acc);
+  if (r < rows) {
+    const uint4* row = reinterpret_cast<const uint4*>(basis + (size_t)r * K);
+#pragma unroll
+    for (int j = 0; j < kVecsPerRow / 4; ++j) {
+      const int v = sub + 4 * j;
+      const uint4 raw = __ldcs(row + v);   // read once per clip: streaming
+      B e[kVec];
+      memcpy(e, &raw, 16);
+#pragma unroll
+      for (int i = 0; i < kVec; ++i) acc += (double)e[i] * cs[v * kVec + i];
+    }
+  }
+  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+  acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+  if (r < rows && sub == 0) {
+    acc += mean[r];
+    const int axis = r % 3;
+    acc -= (axis == 0) ? c0 : (axis == 1 ? c1 : c2);
+    out[r] = static_cast<O>(acc);
+  }
 }
 
 int launch_identity(vp_model* m, const float* id_dev, const float* tex_dev, cudaStream_t st) {
-  const int grid = (m->rows + 255) / 256;
+  const int grid = (4 * m->rows + 255) / 256;
   if (id_dev) {
     if (m->idb64)
       identity_kernel<double, double, VP_N_ID><<<grid, 256, 0, st>>>(

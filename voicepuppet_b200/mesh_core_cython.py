@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ['render_colors_core', 'rasterize_triangles_core']
+__all__ = ['render_colors_core', 'rasterize_triangles_core', 'render_texture_core', 'get_normal_core']
 
 
 def _buffer(name, a, dtype, ndim):
@@ -94,3 +94,43 @@ def rasterize_triangles_core(vertices, triangles, depth_buffer, triangle_buffer,
   _lib.check(_lib.lib().vp_rasterize_triangles_core(_lib.ptr(vertices), _lib.ptr(triangles), _lib.ptr(depth_buffer),
                                                     _lib.ptr(triangle_buffer), _lib.ptr(barycentric_weight), nver,
                                                     ntri, h, w))
+
+
+def render_texture_core(image, vertices, triangles, texture, tex_coords, tex_triangles, depth_buffer, nver, tex_nver,
+                        ntri, h, w, c, tex_h, tex_w, tex_c, mapping_type):
+  """mesh_core_cython.pyx:80-99 -> mesh_core.cpp:234-333 (z-buffer of rasterize_triangles_core, the
+  winner's texel sampled nearest / bilinearly; the texture y coordinate is read with the mesh vertex
+  index like the reference does, mesh_core.cpp:270-272)."""
+  image = _buffer('image', image, np.float32, 3)
+  vertices = _buffer('vertices', vertices, np.float32, 2)
+  triangles = _buffer('triangles', triangles, np.int32, 2)
+  texture = _buffer('texture', texture, np.float32, 3)
+  tex_coords = _buffer('tex_coords', tex_coords, np.float32, 2)
+  tex_triangles = _buffer('tex_triangles', tex_triangles, np.int32, 2)
+  depth_buffer = _buffer('depth_buffer', depth_buffer, np.float32, 2)
+  nver, tex_nver, ntri, h, w, c = int(nver), int(tex_nver), int(ntri), int(h), int(w), int(c)
+  tex_h, tex_w, tex_c, mapping_type = int(tex_h), int(tex_w), int(tex_c), int(mapping_type)
+  _need('image', image, h * w * c)
+  _need('vertices', vertices, 3 * nver)
+  _need('triangles', triangles, 3 * ntri)
+  _need('texture', texture, tex_h * tex_w * tex_c)
+  _need('tex_coords', tex_coords, 3 * tex_nver)
+  _need('tex_triangles', tex_triangles, 3 * ntri)
+  _need('depth_buffer', depth_buffer, h * w)
+  _lib.check(_lib.lib().vp_render_texture_core(_lib.ptr(image), _lib.ptr(vertices), _lib.ptr(triangles),
+                                               _lib.ptr(texture), _lib.ptr(tex_coords), _lib.ptr(tex_triangles),
+                                               _lib.ptr(depth_buffer), nver, tex_nver, ntri, h, w, c, tex_h, tex_w,
+                                               tex_c, mapping_type))
+
+
+def get_normal_core(normal, tri_normal, triangles, ntri):
+  """mesh_core_cython.pyx:40-47 -> mesh_core.cpp:85-105: normal[v] += tri_normal[i] over the corners of every
+  triangle, in ascending triangle order (float32, bit-identical to the reference's loop)."""
+  normal = _buffer('normal', normal, np.float32, 2)
+  tri_normal = _buffer('tri_normal', tri_normal, np.float32, 2)
+  triangles = _buffer('triangles', triangles, np.int32, 2)
+  ntri = int(ntri)
+  _need('tri_normal', tri_normal, 3 * ntri)
+  _need('triangles', triangles, 3 * ntri)
+  _lib.check(_lib.lib().vp_get_normal_core(_lib.ptr(normal), _lib.ptr(tri_normal), _lib.ptr(triangles),
+                                           normal.size // 3, ntri))

@@ -160,6 +160,20 @@ int vp_topology_sizes(const vp_topology* t, int* ntiles, int* nltri, int* nhalo)
 int vp_topology_copy(const vp_topology* t, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
                      int* halo, uint16_t* ring, uint32_t* fan);
 
+/* Post-raster composite of the frame loop, on the device (voicepuppet/pixrefer/infer_bfmvid.py:111-121 and
+ * :234-236): the rasterized frames are resized to size x size exactly like cv2.resize does for 8-bit images
+ * (fixed-point bilinear; 2x2 area mean for an exact 2x downscale), pasted at (x0, y0) into a zero canvas and
+ * written as  canvas[T][H][W][3] uint8 (render_face's return value; channels swapped when swap_rb, :111)  and/or
+ * inputs[T][H][W][in_channels] float32, channels channel_offset..+2 = raster / 255 in the raster's own channel
+ * order (what lands in PixReferNet's inputs[..., 3:6]).  All pointers are device pointers; asynchronous on
+ * `stream`.  A face that does not fit the canvas is VP_ERR_ARG (numpy raises at :121).
+ * vp_composite_placement evaluates :80-82 and :112-121: size = round(res / (ratio * tp[2])), x0 / y0. */
+int vp_composite_placement(int res, int center_x, int center_y, double ratio, const double* transform_params5,
+                           int* size, int* x0, int* y0);
+int vp_composite_dev(const unsigned char* frames_dev, int nframes, int res, int size, int x0, int y0,
+                     int canvas_h, int canvas_w, unsigned char* canvas_dev, int swap_rb, float* inputs_dev,
+                     int in_channels, int channel_offset, int device, void* stream);
+
 /* Expression-basis kernel selection: 0 = automatic (FP32 streamed kernel below 16 frames per launch,
  * tcgen05 3xTF32 GEMM from 16 frames up), 1 = always FP32 SIMT, 2 = always tcgen05 3xTF32. */
 int vp_set_basis_mode(vp_model* m, int mode);

@@ -120,6 +120,10 @@ struct vp_model {
   // workspaces (grow only)
   vp::DevBuf ws_fshared, ws_ex, ws_params, ws_disp, ws_vrec, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
   uint32_t key_epoch = 0;       // epoch of the last chunk rendered into ws_keys (0 = buffer must be cleared)
+  // page-locked staging of the per-frame inputs (so their upload is a real async copy)
+  void* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  cudaEvent_t ev_stage = nullptr;  // recorded after the uploads that read h_stage
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 

@@ -79,6 +79,8 @@ void free_model(vp_model* m) {
     if (m->ev_copy[i]) cudaEventDestroy(m->ev_copy[i]);
   }
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->ev_stage) cudaEventDestroy(m->ev_stage);
+  if (m->h_stage) cudaFreeHost(m->h_stage);
   (void)cudaGetLastError();
   delete m;
 }
@@ -176,6 +178,7 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
   if (basis_tc_prepare(m) != VP_OK) m->have_tmap = false;  // the SIMT kernel still works; mode 2 reports it
 
   VP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  VP_CUDA(cudaEventCreateWithFlags(&m->ev_stage, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     VP_CUDA(cudaEventCreateWithFlags(&m->ev_render[i], cudaEventDisableTiming));
     VP_CUDA(cudaEventCreateWithFlags(&m->ev_copy[i], cudaEventDisableTiming));

@@ -5,6 +5,7 @@
 // launches are K1 basis -> K2 vertex -> K3 scatter -> K4 resolve.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "launch.h"
@@ -209,23 +210,42 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
   VP_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  // per-frame inputs: one upload for the whole sequence (T * 448 bytes)
-  std::vector<FrameParams> hp((size_t)T);
+  // per-frame inputs: one upload for the whole sequence (T * 448 bytes) out of page-locked staging, so
+  // that the copies are asynchronous; the staging is reused only after the previous call's uploads ran
+  const size_t params_bytes = (size_t)T * sizeof(FrameParams), ex_bytes = fr->ex ? (size_t)T * VP_N_EX * sizeof(float) : 0;
+  if (m->h_stage_cap < params_bytes + ex_bytes) {
+    if (m->h_stage) {
+      VP_CUDA(cudaEventSynchronize(m->ev_stage));
+      cudaFreeHost(m->h_stage);
+      m->h_stage = nullptr;
+      m->h_stage_cap = 0;
+    }
+    const size_t want = std::max<size_t>(2 * (params_bytes + ex_bytes), 1 << 16);
+    VP_CUDA(cudaHostAlloc(&m->h_stage, want, cudaHostAllocDefault));
+    m->h_stage_cap = want;
+  } else {
+    VP_CUDA(cudaEventSynchronize(m->ev_stage));
+  }
+  FrameParams* hp = static_cast<FrameParams*>(m->h_stage);
   for (int t = 0; t < T; ++t) {
     for (int k = 0; k < 9; ++k) hp[t].rot[k] = fr->rotation[9 * (size_t)t + k];
     for (int k = 0; k < 3; ++k) hp[t].trans[k] = fr->translation[3 * (size_t)t + k];
     for (int k = 0; k < VP_N_GAMMA; ++k) hp[t].gamma[k] = fr->gamma[VP_N_GAMMA * (size_t)t + k];
   }
-  VP_CUDA(m->ws_params.reserve((size_t)T * sizeof(FrameParams), m->device));
-  VP_CUDA(cudaMemcpyAsync(m->ws_params.ptr, hp.data(), (size_t)T * sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+  VP_CUDA(m->ws_params.reserve(params_bytes, m->device));
+  VP_CUDA(cudaMemcpyAsync(m->ws_params.ptr, hp, params_bytes, cudaMemcpyHostToDevice, st));
   if (fr->ex) {
-    VP_CUDA(m->ws_ex.reserve((size_t)T * VP_N_EX * sizeof(float), m->device));
-    VP_CUDA(cudaMemcpyAsync(m->ws_ex.ptr, fr->ex, (size_t)T * VP_N_EX * sizeof(float), cudaMemcpyHostToDevice, st));
+    float* hex = reinterpret_cast<float*>(static_cast<char*>(m->h_stage) + params_bytes);
+    std::memcpy(hex, fr->ex, ex_bytes);
+    VP_CUDA(m->ws_ex.reserve(ex_bytes, m->device));
+    VP_CUDA(cudaMemcpyAsync(m->ws_ex.ptr, hex, ex_bytes, cudaMemcpyHostToDevice, st));
   }
+  VP_CUDA(cudaEventRecord(m->ev_stage, st));
   const float* ex_dev = fr->ex ? m->ws_ex.as<float>() : nullptr;
   const FrameParams* params_dev = m->ws_params.as<FrameParams>();
 
   const int chunk = chunk_frames(m, res, T, outputs_on_device == 0);
+  const bool forced_chunk = env_size("VPB200_CHUNK_FRAMES", 0) != 0;
   const int group = basis_group_frames(chunk, T);
   VP_TRY(reserve_chunk(m, chunk, group, res));
   const size_t npix = (size_t)res * res;
@@ -247,9 +267,13 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
       VP_CUDA(m->ws_img[b].reserve((size_t)chunk * npix * 3, m->device));
       if (face_mask) VP_CUDA(m->ws_mask[b].reserve((size_t)chunk * npix, m->device));
     }
+    // The drain over PCIe (about 3.5 us per 256x256 frame) is the slow side of this pipeline, so what matters
+    // is how soon it starts: the first chunk is short, the following ones full-sized.
+    const int first = (forced_chunk || T < 4 * 8) ? chunk : std::max(6, chunk / 3);
     int ci = 0;
-    for (int t0 = 0; t0 < T && rc == VP_OK; t0 += chunk, ++ci) {
-      const int n = std::min(chunk, T - t0);
+    for (int t0 = 0, n = 0; t0 < T && rc == VP_OK; t0 += n, ++ci) {
+      n = std::min(t0 == 0 ? first : chunk, T - t0);
+      if (t0 / group != (t0 + n - 1) / group) n = (t0 / group + 1) * group - t0;  // chunks do not straddle basis groups
       const int b = ci & 1;
       if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(st, m->ev_copy[b], 0));
       if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, T, group, st, prof);

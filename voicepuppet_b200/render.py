@@ -373,21 +373,87 @@ def rasterize_face(bfmcoeff, facemodel, res=IMG):
   return np.asarray(render_sequence(np.asarray(bfmcoeff).reshape(1, 257), facemodel, res=res, angles=ang)[0])
 
 
+def composite_placement(center_x, center_y, ratio, transform_params, res=IMG):
+  """infer_bfmvid.py:80-82,112-121: (S, x0, y0) -- side of the resized face and its top-left corner in the canvas."""
+  import ctypes
+  from . import _lib
+  tp = np.ascontiguousarray(np.asarray(transform_params, dtype=np.float64).reshape(-1)[:5])
+  if tp.size != 5:
+    raise ValueError('transform_params must hold 5 values (w0, h0, s, tx, ty)')
+  size, x0, y0 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+  _lib.check(_lib.lib().vp_composite_placement(int(res), int(center_x), int(center_y), float(ratio), _lib.ptr(tp),
+                                               ctypes.byref(size), ctypes.byref(x0), ctypes.byref(y0)))
+  return size.value, x0.value, y0.value
+
+
+def composite_device(frames, center_x, center_y, ratio, transform_params, canvas_hw=(512, 512), inputs=None,
+                     channel_offset=3, want_canvas=True):
+  """The post-raster part of render_face and of the frame loop (infer_bfmvid.py:111-121, 234-236) for a batch
+  of rasterized frames, on the GPU: cv2.resize-exact bilinear resize, paste into a zero canvas, and the
+  float32 / 255 image PixReferNet reads.
+
+  frames   torch uint8 [T,res,res,3] on a CUDA device (as written by the rasterizer)
+  inputs   optional torch float32 [T,H,W,C] on the same device; channels channel_offset..+2 are overwritten
+           (the frame loop's ``inputs[0, ..., 3:6] = face3d``), the others are left alone
+  Returns (canvas uint8 [T,H,W,3] with render_face's channel order, or None; inputs or None).
+  Asynchronous on the current torch stream."""
+  import ctypes
+  import torch
+  from . import _lib
+  if not (frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+          and frames.shape[1] == frames.shape[2] and frames.is_contiguous()):
+    raise ValueError('frames must be a contiguous uint8 CUDA tensor [T,res,res,3]')
+  t, res = int(frames.shape[0]), int(frames.shape[1])
+  h, w = int(canvas_hw[0]), int(canvas_hw[1])
+  size, x0, y0 = composite_placement(center_x, center_y, ratio, transform_params, res)
+  canvas = torch.empty((t, h, w, 3), dtype=torch.uint8, device=frames.device) if want_canvas else None
+  in_c = 0
+  if inputs is not None:
+    if not (inputs.is_cuda and inputs.dtype == torch.float32 and inputs.is_contiguous() and inputs.dim() == 4
+            and tuple(inputs.shape[:3]) == (t, h, w) and inputs.device == frames.device):
+      raise ValueError('inputs must be a contiguous float32 CUDA tensor [T,%d,%d,C] on the frames\' device' % (h, w))
+    in_c = int(inputs.shape[3])
+  if canvas is None and inputs is None:
+    raise ValueError('nothing to produce: pass inputs or want_canvas=True')
+  stream = ctypes.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
+  _lib.check(_lib.lib().vp_composite_dev(
+      ctypes.c_void_p(frames.data_ptr()), t, res, size, x0, y0, h, w,
+      None if canvas is None else ctypes.c_void_p(canvas.data_ptr()), 1,
+      None if inputs is None else ctypes.c_void_p(inputs.data_ptr()), in_c, int(channel_offset),
+      frames.device.index, stream))
+  return canvas, inputs
+
+
+def render_face_sequence(center_x, center_y, ratio, coeffs, img_shape, transform_params, facemodel, inputs=None,
+                         channel_offset=3, angles='jitter', device=0, want_canvas=True):
+  """The frame loop of infer_bfmvid.py:231-236 for a whole coefficient sequence, entirely on the GPU:
+  reconstruct + rasterize T frames at 224x224 (render_face, :79-109), resize / paste them into the
+  identity image's canvas (:111-121) and write face3d = canvas / 255 into ``inputs[..., 3:6]`` -- the tensor
+  PixReferNet is fed with -- without a host round trip.  Returns (canvas [T,H,W,3] uint8 CUDA tensor with
+  render_face's channel order or None, inputs)."""
+  import torch
+  coeffs = np.ascontiguousarray(np.asarray(coeffs, dtype=np.float32))
+  t = coeffs.shape[0]
+  dev = torch.device('cuda', device)
+  frames = torch.empty((t, IMG, IMG, 3), dtype=torch.uint8, device=dev)
+  with torch.cuda.device(dev):
+    render_sequence(coeffs, facemodel, res=IMG, angles=angles, device=device, out=frames)
+    return composite_device(frames, center_x, center_y, ratio, transform_params, (img_shape[0], img_shape[1]),
+                            inputs, channel_offset, want_canvas)
+
+
 def render_face(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel):
-  """Same signature and result as infer_bfmvid.py:79-122.  Everything up to the rasterized 224x224
-  frame runs on the GPU; the channel swap, cv2.resize and paste into the canvas are the reference's
-  own cv2 calls on the host."""
-  import cv2
-  ratio *= transform_params[2]
-  tx = -int((transform_params[3] / ratio))
-  ty = -int((transform_params[4] / ratio))
-  new_image = rasterize_face(bfmcoeff, facemodel, IMG)
-  new_image = cv2.cvtColor(new_image, cv2.COLOR_BGR2RGB)
-  new_image = cv2.resize(new_image, (int(round(new_image.shape[0] / ratio)), int(round(new_image.shape[1] / ratio))))
-  back_new_image = np.zeros((img.shape[0], img.shape[1], img.shape[2]), dtype=img.dtype)
-  center_face_x = new_image.shape[1] // 2
-  center_face_y = new_image.shape[0] // 2
-  ry = center_y - center_face_y + new_image.shape[0] - ty
-  rx = center_x - center_face_x + new_image.shape[1] - tx
-  back_new_image[center_y - center_face_y - ty:ry, center_x - center_face_x - tx:rx, :] = new_image
-  return back_new_image
+  """Same signature and result as infer_bfmvid.py:79-122 (one frame, jitter globals advanced): reconstruction,
+  rasterization, channel swap, cv2.resize-exact resize and paste all run on the GPU; the returned canvas is a
+  numpy uint8 array of ``img``'s shape, like the reference's."""
+  import torch
+  ang = _state.step().copy()
+  dev = torch.device('cuda', 0)
+  frames = torch.empty((1, IMG, IMG, 3), dtype=torch.uint8, device=dev)
+  with torch.cuda.device(dev):
+    render_sequence(np.asarray(bfmcoeff).reshape(1, 257), facemodel, res=IMG, angles=ang, device=0, out=frames)
+    try:
+      canvas, _ = composite_device(frames, center_x, center_y, ratio, transform_params, (img.shape[0], img.shape[1]))
+    except Exception as e:   # numpy raises ValueError when the face does not fit the canvas (:121)
+      raise ValueError(str(e))
+  return canvas[0].cpu().numpy().astype(img.dtype, copy=False)

@@ -54,6 +54,16 @@ def algorithmic_bytes(t, res):
   return per_kernel, total
 
 
+def ncu_traffic():
+  """Per-launch DRAM traffic of the hot kernels from the committed ncu --set full capture of this workload
+  (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None when absent or for another workload."""
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+      return json.load(f)
+  except Exception:
+    return {}
+
+
 def measured_peaks():
   path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   try:
@@ -128,7 +138,11 @@ def cpu_reference_run(frames, res, steps, warmup):
   synthetic.cached_model()                                    # build / cache before forking
   coeffs = synthetic.make_coeffs(frames, seed=1)
   angles = orc.jitter_angle_sequence(frames)[:, 0, :]
-  kind = pipeline.rasterizer()[1]
+  raster_kind = pipeline.rasterizer()[1]
+  # reconstruct_mesh.py is Python and does not exist on the GPU box: its numpy restatement (pinned bit for bit
+  # to the live reference, tests/test_oracle_reconstruct.py) runs instead -> "port"; the rasterizer is the
+  # reference's own mesh_core.cpp compiled in place when oracle/_ref travelled with the snapshot
+  kind = 'port'
   times = []
   import multiprocessing as mp
   ctx = mp.get_context('fork')
@@ -143,7 +157,8 @@ def cpu_reference_run(frames, res, steps, warmup):
       if i >= warmup:
         times.append(dt)
   sec = sum(times) / len(times)
-  return {'fps': frames / sec, 'sec_per_step': sec, 'cores': workers, 'kind': kind, 'frames': frames}
+  return {'fps': frames / sec, 'sec_per_step': sec, 'cores': workers, 'kind': kind, 'frames': frames,
+          'raster_kind': raster_kind}
 
 
 def run_reference_arm(args):
@@ -153,7 +168,8 @@ def run_reference_arm(args):
   r = cpu_reference_run(args.frames, args.res, args.steps, args.warmup)
   sample = '%d frames at %dx%d per step over %d worker processes (%s rasterizer)' % (
       r['frames'], args.res, args.res, r['cores'],
-      "the reference's own mesh_core.cpp" if r['kind'] == 'reference' else 'C restatement of mesh_core.cpp')
+      "numpy restatement of reconstruct_mesh.py + the reference's own mesh_core.cpp" if r['raster_kind'] == 'reference'
+      else 'numpy restatement of reconstruct_mesh.py + C restatement of mesh_core.cpp')
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': r['fps'], 'unit': 'frames/s', 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * r['sec_per_step'], 'higher_is_better': True,
@@ -223,7 +239,8 @@ def run_ours(args):
     if world == 1:
       render.render_device(dm, ex_dev, params_dev, True, res, frames_dev, mask_dev)
     elif peer is not None:   # every rank's resolve kernel stores straight into rank 0's buffer over NVLink
-      peer.render_into(dm, ex_dev, params_dev, True, mode=os.environ.get('VPB200_PEER_MODE', 'auto'))
+      peer.render_into(dm, ex_dev, params_dev, True, mode=os.environ.get('VPB200_PEER_MODE', 'auto'),
+                       notify_frames=int(os.environ['VPB200_NOTIFY_FRAMES']) if 'VPB200_NOTIFY_FRAMES' in os.environ else None)
     else:                    # baseline: render locally, NCCL gather to rank 0
       render.pipelined_gather(dm, ex_dev, params_dev, True, res, frames_dev, world, rank)
 
@@ -318,14 +335,23 @@ def run_ours(args):
         kernels[k] = {'ms': round(ms, 5), 'algorithmic_bytes': per_kernel_bytes[k], 'gbs': round(gbs, 1),
                       'frac': round(gbs / peak, 4)}
     if dominant:
+      traffic = ncu_traffic() if (t_local == 75 and res == 256) else {}
+      for k in kernels:
+        kernels[k]['traffic'] = traffic.get(k)
       roofline = {'bound': 'hbm', 'kernel': dominant, 'achieved': kernels[dominant]['gbs'], 'peak': peak,
-                  'unit': 'GB/s', 'frac': kernels[dominant]['frac'], 'traffic': None, 'peak_source': peak_src}
+                  'unit': 'GB/s', 'frac': kernels[dominant]['frac'], 'traffic': traffic.get(dominant),
+                  'traffic_source': traffic.get('source'), 'peak_source': peak_src,
+                  'note': 'dominant kernel by duration; it is bound by the LSU data pipe / instruction issue, not by '
+                          'HBM (profiles/): the HBM-bound kernels of the path are basis and resolve, see "kernels"'}
     pipeline_gbs = total_bytes / (ms_per_step * 1e-3) / 1e9
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
       r = cpu_reference_run(args.cpu_frames, res, 1, 1)
       cpu = {'value': r['fps'], 'unit': 'frames/s', 'cores': r['cores'], 'kind': r['kind'],
-             'sample': '%d frames at %dx%d, one pass over %d worker processes' % (r['frames'], res, res, r['cores'])}
+             'sample': '%d frames at %dx%d, one pass over %d worker processes (numpy restatement of reconstruct_mesh.py'
+                       ' + %s)' % (r['frames'], res, res, r['cores'],
+                                   "the reference's own mesh_core.cpp" if r['raster_kind'] == 'reference'
+                                   else 'C restatement of mesh_core.cpp')}
     line = {
         'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',

@@ -270,6 +270,13 @@ int vp_render_sequence_dev_notify(vp_model* m, int nframes, const float* ex_dev,
                                   unsigned char* image_dev, unsigned char* face_mask_dev, void* stream,
                                   int notify_frames, void** events, int nevents);
 
+/* Same with an explicit plan: chunk i renders chunk_frames[i] frames (they add up to nframes) and
+ * events[i] is recorded when it is complete. */
+int vp_render_sequence_dev_chunks(vp_model* m, int nframes, const float* ex_dev,
+                                  const vp_frame_params* params_dev, int rotate_shape_first, int res,
+                                  unsigned char* image_dev, unsigned char* face_mask_dev, void* stream,
+                                  const int* chunk_frames, int nchunks, void** events);
+
 /* The expression contraction alone (device pointers, asynchronous on `stream`):
  * disp_dev[t][r] = sum_k exBase[r][k] * ex_dev[t][k], r in the library's internal row order
  * (3 * internal vertex + axis), vp_model_rows_pad() floats per frame. */

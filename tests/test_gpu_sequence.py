@@ -111,3 +111,26 @@ def test_render_face_drop_in(full_model):
   d = np.abs(face.astype(np.int16) - want.astype(np.int16))
   assert np.percentile(d, 99.5) <= 1
   assert not out[:100].any()
+
+
+def test_contact_sheet_matches_cpu_reference(small_model, tmp_path):
+  """plot_bfm_coeff_seq (utils/bfm_visual.py:88-154): 2 x up to 30 frames through Reconstruction (coefficient
+  angles), tiled 10 per row, predicted rows start at row 3; identity varies per frame in the real sequence."""
+  from voicepuppet_b200 import bfm_visual
+  t = 13
+  real = synthetic.make_coeffs(t, seed=11)[None]
+  real[0, 5:, :80] = synthetic.make_coeffs(1, seed=12)[0, :80]      # two identity runs
+  pred = synthetic.make_coeffs(t, seed=13)[None, :, 80:144]
+  sheet = bfm_visual.contact_sheet(small_model, [t], real, pred)
+  assert sheet.shape == (9 * 224, 10 * 224, 3) and sheet.dtype == np.uint8
+  spliced = np.concatenate([real[:, :, :80], pred, real[:, :, 144:]], axis=2)
+  for seq, h_index in ((real, 0), (spliced, 3)):
+    want = pipeline.render_sequence(np.ascontiguousarray(seq[0]), small_model, 224, None)
+    for i in (0, 7, t - 1):
+      r, c = i // 10 + h_index, i % 10
+      tile = sheet[r * 224:(r + 1) * 224, c * 224:(c + 1) * 224]
+      d = np.abs(tile[:, :, ::-1].astype(np.int16) - want[i].astype(np.int16))
+      assert np.percentile(d, 99.5) <= 1 and (d > 1).mean() < 0.003
+  assert not sheet[6 * 224:].any() and not sheet[2 * 224:3 * 224].any()
+  bfm_visual.plot_bfm_coeff_seq(str(tmp_path), small_model, 1000, [t], real, pred)
+  assert (tmp_path / 'bfmnet_1000.jpg').stat().st_size > 1000

@@ -34,7 +34,20 @@ print('| kernel | ' + ' | '.join(short(h) for h in keep) + ' |')
 print('|---|' + '---|' * len(keep))
 for r in data:
   print('| %s | ' % r[idx['Kernel Name']].split('(')[0].split('::')[-1][:40] + ' | '.join('%.2f' % g(r, h, 0) for h in keep) + ' |')
-if len(sys.argv) > 2:
+KERNEL_SLOTS = (('basis_tc_kernel', 'basis'), ('basis_simt_kernel', 'basis'), ('vertex_fan_kernel', 'vertex'),
+                ('vertex_tile_kernel', 'vertex'), ('raster_scatter', 'scatter'), ('resolve_packed_kernel', 'resolve'))
+if '--traffic-json' in sys.argv:   # per-launch DRAM traffic of the hot kernels, read back by bench.py
+  import json
+  out_path = sys.argv[sys.argv.index('--traffic-json') + 1]
+  traffic = {'source': rep.split('/')[-1], 'note': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 75 frames at 256x256'}
+  for r in data:
+    for pat, slot in KERNEL_SLOTS:
+      if pat in r[idx['Kernel Name']]:
+        traffic[slot] = int(scale(r, 'dram__bytes_read.sum') + scale(r, 'dram__bytes_write.sum'))
+  json.dump(traffic, open(out_path, 'w'), indent=1)
+args = [a for a in sys.argv[2:] if not a.startswith('--') and not a.endswith('.json')]
+if args:
+  sys.argv = sys.argv[:2] + args
   lr = list(csv.DictReader(l for l in open(sys.argv[2]) if l.startswith('"')))
   agg = collections.OrderedDict()
   for r in lr:

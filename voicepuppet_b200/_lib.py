@@ -93,6 +93,7 @@ SIGNATURES = {
     'vp_render_sequence': (_i, [_vp, ctypes.POINTER(VpFrames), _i, _vp, _vp, _i, _vp]),
     'vp_render_sequence_dev': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     'vp_render_sequence_dev_notify': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i]),
+    'vp_render_sequence_dev_chunks': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     'vp_basis_dev': (_i, [_vp, _vp, _vp, _i, _vp]),
     'vp_model_rows_pad': (_i, [_vp]),
     'vp_debug_basis_trace': (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -124,6 +124,10 @@ struct vp_model {
   void* h_stage = nullptr;
   size_t h_stage_cap = 0;
   cudaEvent_t ev_stage = nullptr;  // recorded after the uploads that read h_stage
+  // second compute stream: consecutive chunks alternate between the caller's stream and this one (and between
+  // the two halves of the chunk workspaces), so the ramp-up of one chunk's kernels fills the tails of the other's
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_basis = nullptr, ev_aux_done = nullptr, ev_main_done = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 
@@ -151,8 +155,11 @@ int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nfram
 enum BasisMode { kBasisAuto = 0, kBasisSimt = 1, kBasisTensor = 2 };
 constexpr int kBasisTensorMinFrames = 16;  // below this the frame batch is a GEMV, not a dense contraction
 // disp_dev may be NULL (no expression displacement).  vrec_dev may be NULL (no raster records).
+// frame_constants: NULL (prepared here from params_dev) or this chunk's slice of prepare_frame_constants().
 int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes,
                   int rotate_first, double focal, double center, double image_size, double raster_scale,
-                  float4* vrec_dev, const ReconOut& out, cudaStream_t st);
+                  float4* vrec_dev, const ReconOut& out, cudaStream_t st, const void* frame_constants = nullptr);
+int prepare_frame_constants(vp_model* m, const FrameParams* params_dev, int nframes, cudaStream_t st, const void** out);
+size_t frame_constants_stride();
 
 }  // namespace vp

@@ -80,6 +80,9 @@ void free_model(vp_model* m) {
   }
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->ev_stage) cudaEventDestroy(m->ev_stage);
+  for (cudaEvent_t e : {m->ev_fork, m->ev_basis, m->ev_aux_done, m->ev_main_done})
+    if (e) cudaEventDestroy(e);
+  if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   (void)cudaGetLastError();
   delete m;
@@ -179,6 +182,9 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
 
   VP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   VP_CUDA(cudaEventCreateWithFlags(&m->ev_stage, cudaEventDisableTiming));
+  VP_CUDA(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t* e : {&m->ev_fork, &m->ev_basis, &m->ev_aux_done, &m->ev_main_done})
+    VP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     VP_CUDA(cudaEventCreateWithFlags(&m->ev_render[i], cudaEventDisableTiming));
     VP_CUDA(cudaEventCreateWithFlags(&m->ev_copy[i], cudaEventDisableTiming));

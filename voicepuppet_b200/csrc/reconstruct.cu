@@ -542,9 +542,23 @@ __global__ void __launch_bounds__(kTileV, 5) vertex_tile_kernel(const VertexArgs
   }
 }
 
+// Per-frame constants of `nframes` frames into m->ws_fshared (one launch per sequence); the returned pointer,
+// advanced by frame_constants_stride() per frame, is what launch_vertex takes as `frame_constants`.
+int prepare_frame_constants(vp_model* m, const FrameParams* params_dev, int nframes, cudaStream_t st, const void** out) {
+  *out = nullptr;
+  if (nframes == 0) return VP_OK;
+  VP_CUDA(m->ws_fshared.reserve((size_t)nframes * sizeof(FrameShared), m->device));
+  FrameShared* fshared = m->ws_fshared.as<FrameShared>();
+  frame_prep_kernel<<<(nframes + 3) / 4, 256, 0, st>>>(params_dev, fshared, nframes);
+  VP_LAUNCH_CHECK();
+  *out = fshared;
+  return VP_OK;
+}
+size_t frame_constants_stride() { return sizeof(FrameShared); }
+
 int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes, int rotate_first,
                   double focal, double center, double image_size, double raster_scale, float4* vrec_dev,
-                  const ReconOut& out, cudaStream_t st) {
+                  const ReconOut& out, cudaStream_t st, const void* frame_constants) {
   if (nframes == 0 || m->ntiles == 0) return VP_OK;
   VertexArgs a;
   a.tiles = m->tiles;
@@ -558,11 +572,9 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.tex = m->have_tex ? m->tex : nullptr;
   a.disp = disp_dev;
   a.disp_stride = (size_t)m->rows_pad;
-  VP_CUDA(m->ws_fshared.reserve((size_t)nframes * sizeof(FrameShared), m->device));
-  FrameShared* fshared = m->ws_fshared.as<FrameShared>();
-  frame_prep_kernel<<<(nframes + 3) / 4, 256, 0, st>>>(params_dev, fshared, nframes);
-  VP_LAUNCH_CHECK();
-  a.fshared = fshared;
+  const void* prepared = frame_constants;
+  if (prepared == nullptr) VP_TRY(prepare_frame_constants(m, params_dev, nframes, st, &prepared));
+  a.fshared = static_cast<const FrameShared*>(prepared);
   a.nframes = nframes;
   a.rotate_first = rotate_first;
   a.has_out = (out.shape || out.norm || out.color || out.proj || out.zbuf) ? 1 : 0;

@@ -82,53 +82,120 @@ int basis_group_frames(int chunk, int nframes) {
   return (per_group + chunk - 1) / chunk * chunk;  // a whole number of raster chunks
 }
 
-int reserve_chunk(vp_model* m, int chunk, int group, int res) {
-  const size_t npix = (size_t)res * res;
-  VP_CUDA(m->ws_disp.reserve((size_t)group * m->rows_pad * sizeof(float), m->device));  // >= any group
-  VP_CUDA(m->ws_vrec.reserve((size_t)chunk * m->vrec_stride * sizeof(float4), m->device));
-  VP_CUDA(m->ws_tricol.reserve((size_t)chunk * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
-  const size_t key_bytes = (size_t)chunk * npix * sizeof(unsigned long long);
-  void* before = m->ws_keys.ptr;
-  VP_CUDA(m->ws_keys.reserve(key_bytes, m->device));
-  if (m->ws_keys.ptr != before) m->key_epoch = 0;
-  return VP_OK;
-}
+// Issues the chunks of one sequence.  With `dual`, consecutive chunks alternate between the caller's stream
+// and the model's auxiliary stream, and between the two halves ("slots") of the chunk workspaces: a chunk is
+// three dependent kernels of a few tens of microseconds, each with a ramp-up and a tail during which most
+// SMs idle; with two chunks in flight the other chunk's kernels fill those gaps (measured on B200: 25-frame
+// chunks cost 66 us each on one stream against 52 us of work).  Everything is joined back onto the caller's
+// stream in finish(), so the call stays stream-ordered for the caller.
+struct ChunkRunner {
+  vp_model* m;
+  cudaStream_t st;
+  Profiler prof;
+  int res = 0, chunk_cap = 0, group = 0, nframes = 0, rotate_first = 0;
+  const float* ex_dev = nullptr;
+  const FrameParams* params_dev = nullptr;
+  const char* fconst = nullptr;
+  bool dual = false, aux_used = false, aux_needs_basis = false;
+  int issued = 0;
 
-// one chunk, everything on the device, nothing synchronised; disp_dev holds this chunk's displacements
-int render_chunk(vp_model* m, int n, const float* disp_dev, const FrameParams* params_dev, int rotate_first, int res,
-                 unsigned char* image_dev, unsigned char* mask_dev, cudaStream_t st, Profiler& prof) {
-  // every chunk gets a fresh epoch; stale keys lose every atomicMax and read as background
-  if (m->key_epoch == 0 || m->key_epoch >= epoch_limit(m->ntri)) {
-    VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
-    m->key_epoch = 0;
+  ChunkRunner(vp_model* m_, cudaStream_t st_) : m(m_), st(st_), prof(m_, st_) {}
+
+  int init(int nframes_, int res_, int chunk_cap_, int nchunks, const float* ex, const FrameParams* params,
+           int rotate_first_, bool allow_dual = true) {
+    nframes = nframes_;
+    res = res_;
+    chunk_cap = chunk_cap_;
+    ex_dev = ex;
+    params_dev = params;
+    rotate_first = rotate_first_;
+    group = basis_group_frames(chunk_cap, nframes);
+    static const int dual_env = [] { const char* e = std::getenv("VPB200_DUAL"); return e ? std::atoi(e) : 1; }();
+    dual = allow_dual && dual_env != 0 && nchunks >= 2 && !m->profiling && (uint32_t)nchunks + 4u < epoch_limit(m->ntri);
+    const int slots = dual ? 2 : 1;
+    const size_t npix = (size_t)res * res;
+    VP_CUDA(m->ws_disp.reserve((size_t)group * m->rows_pad * sizeof(float), m->device));  // >= any group
+    VP_CUDA(m->ws_vrec.reserve((size_t)slots * chunk_cap * m->vrec_stride * sizeof(float4), m->device));
+    VP_CUDA(m->ws_tricol.reserve((size_t)slots * chunk_cap * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
+    void* before = m->ws_keys.ptr;
+    VP_CUDA(m->ws_keys.reserve((size_t)slots * chunk_cap * npix * sizeof(unsigned long long), m->device));
+    if (m->ws_keys.ptr != before) m->key_epoch = 0;
+    // every chunk gets a fresh epoch; stale keys lose every atomicMax and read as background.  The z-buffer is
+    // cleared only when the epoch counter would wrap during this call (or the buffer is new)
+    if (m->key_epoch == 0 || m->key_epoch + (uint32_t)nchunks + 2u >= epoch_limit(m->ntri)) {
+      VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
+      m->key_epoch = 0;
+    }
+    const void* fc = nullptr;
+    VP_TRY(prepare_frame_constants(m, params_dev, nframes, st, &fc));
+    fconst = static_cast<const char*>(fc);
+    if (dual) VP_CUDA(cudaEventRecord(m->ev_fork, st));
+    return VP_OK;
   }
-  const uint32_t epoch = ++m->key_epoch;
-  float4* vrec = m->ws_vrec.as<float4>();
-  unsigned long long* keys = m->ws_keys.as<unsigned long long>();
-  uint32_t* tricol = m->ws_tricol.as<uint32_t>();
-  ReconOut none;
-  prof.begin(kProfVertex);
-  VP_TRY(launch_vertex(m, disp_dev, params_dev, n, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, vrec, none,
-                       st));
-  prof.end();
-  prof.begin(kProfScatter);
-  VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, epoch, n, m->ntri, res, res, st));
-  prof.end();
-  prof.begin(kProfResolve);
-  VP_TRY(launch_resolve_packed(keys, tricol, m->t_orig2int_dev, epoch, image_dev, mask_dev, n, m->ntri, res, res, st));
-  prof.end();
-  return VP_OK;
-}
 
-// frames [t0, t0 + n) start a new basis group: contract the whole group's expression coefficients
-int basis_group(vp_model* m, const float* ex_dev, int t0, int total, int group, cudaStream_t st, Profiler& prof) {
-  if (!ex_dev) return VP_OK;
-  const int n = std::min(group, total - t0);
-  prof.begin(kProfBasis);
-  VP_TRY(launch_basis(m, ex_dev + (size_t)t0 * VP_N_EX, m->ws_disp.as<float>(), n, st));
-  prof.end();
-  return VP_OK;
-}
+  // frames [t0, t0 + n): n <= chunk_cap and inside one basis group.  *used = the stream the chunk runs on.
+  int run(int t0, int n, unsigned char* image_dev, unsigned char* mask_dev, cudaStream_t* used) {
+    if (ex_dev && t0 % group == 0) {  // a new basis group: contract its expression coefficients on `st`
+      if (aux_used) {                 // chunks on the auxiliary stream may still read the previous group
+        VP_CUDA(cudaEventRecord(m->ev_aux_done, m->aux_stream));
+        VP_CUDA(cudaStreamWaitEvent(st, m->ev_aux_done, 0));
+      }
+      const int gn = std::min(group, nframes - t0);
+      prof.begin(kProfBasis);
+      VP_TRY(launch_basis(m, ex_dev + (size_t)t0 * VP_N_EX, m->ws_disp.as<float>(), gn, st));
+      prof.end();
+      if (dual) {
+        VP_CUDA(cudaEventRecord(m->ev_basis, st));
+        aux_needs_basis = true;
+      }
+    }
+    const int slot = dual ? (issued & 1) : 0;
+    cudaStream_t cs = slot ? m->aux_stream : st;
+    if (slot) {
+      if (!aux_used) VP_CUDA(cudaStreamWaitEvent(cs, m->ev_fork, 0));
+      if (aux_needs_basis) VP_CUDA(cudaStreamWaitEvent(cs, m->ev_basis, 0));
+      aux_used = true;
+      aux_needs_basis = false;
+    }
+    ++issued;
+    const uint32_t epoch = ++m->key_epoch;
+    const size_t npix = (size_t)res * res;
+    float4* vrec = m->ws_vrec.as<float4>() + (size_t)slot * chunk_cap * m->vrec_stride;
+    unsigned long long* keys = m->ws_keys.as<unsigned long long>() + (size_t)slot * chunk_cap * npix;
+    uint32_t* tricol = m->ws_tricol.as<uint32_t>() + (size_t)slot * chunk_cap * std::max(m->ntri, 1);
+    const float* disp = ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr;
+    ReconOut none;
+    prof.begin(kProfVertex);
+    VP_TRY(launch_vertex(m, disp, params_dev + t0, n, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, vrec,
+                         none, cs, fconst + (size_t)t0 * frame_constants_stride()));
+    prof.end();
+    prof.begin(kProfScatter);
+    VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, epoch, n, m->ntri, res, res, cs));
+    prof.end();
+    prof.begin(kProfResolve);
+    VP_TRY(launch_resolve_packed(keys, tricol, m->t_orig2int_dev, epoch, image_dev, mask_dev, n, m->ntri, res, res, cs));
+    prof.end();
+    if (used) *used = cs;
+    return VP_OK;
+  }
+
+  // the widest chunk that starts at t0, is at most `want` frames and does not cross a basis group
+  int clip(int t0, int want) const { return std::min(std::min(want, chunk_cap), group - t0 % group); }
+
+  int finish(int rc) {
+    if (aux_used) {  // join: work the caller enqueues on `st` after this call sees every frame
+      cudaError_t e = cudaEventRecord(m->ev_aux_done, m->aux_stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(st, m->ev_aux_done, 0);
+      if (e != cudaSuccess && rc == VP_OK) {
+        set_error("joining the auxiliary stream failed: %s", cudaGetErrorString(e));
+        rc = VP_ERR_CUDA;
+      }
+    }
+    if (rc != VP_OK) m->key_epoch = 0;
+    prof.finish();
+    return rc;
+  }
+};
 
 int check_sequence_args(const vp_model* m, int nframes, int res, const void* image) {
   VP_REQUIRE(m != nullptr, "null model");
@@ -143,46 +210,66 @@ int check_sequence_args(const vp_model* m, int nframes, int res, const void* ima
 
 using namespace vp;
 
+// plan == nullptr: uniform chunks chosen by chunk_frames().  Otherwise plan[0..nplan) are the chunk sizes
+// (sum == nframes) and events[i] is recorded when chunk i is complete; a planned chunk that crosses a basis
+// group boundary is rendered in two launches.
 static int render_sequence_dev_impl(vp_model* m, int nframes, const float* ex_dev, const vp_frame_params* params_dev,
                                     int rotate_shape_first, int res, unsigned char* image_dev,
-                                    unsigned char* face_mask_dev, void* stream, int notify_frames, void** events,
-                                    int nevents) {
+                                    unsigned char* face_mask_dev, void* stream, const int* plan, int nplan,
+                                    void** events) {
   VP_TRY(check_sequence_args(m, nframes, res, image_dev));
   VP_REQUIRE(nframes == 0 || params_dev != nullptr, "null params");
-  VP_REQUIRE(notify_frames >= 0 && (notify_frames == 0 || (events != nullptr && nevents > 0)), "bad notify arguments");
   if (nframes == 0) return VP_OK;
+  int plan_max = 0;
+  if (plan) {
+    VP_REQUIRE(nplan > 0 && events != nullptr, "bad chunk plan");
+    long long sum = 0;
+    for (int i = 0; i < nplan; ++i) {
+      VP_REQUIRE(plan[i] > 0, "chunk sizes must be positive");
+      sum += plan[i];
+      plan_max = std::max(plan_max, plan[i]);
+    }
+    VP_REQUIRE(sum == nframes, "chunk sizes must add up to nframes");
+  }
   std::lock_guard<std::mutex> lock(m->mu);
   VP_REQUIRE(m->have_base && m->have_tex, "no identity set (call vp_set_identity first)");
   VP_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int chunk = notify_frames > 0 ? notify_frames : chunk_frames(m, res, nframes, false);
-  VP_REQUIRE(notify_frames == 0 || (nframes + chunk - 1) / chunk <= nevents, "not enough events for the chunks");
-  const int group = basis_group_frames(chunk, nframes);
-  VP_TRY(reserve_chunk(m, chunk, group, res));
+  const int chunk = plan ? std::min(plan_max, 1024) : chunk_frames(m, res, nframes, false);
+  const int nchunks = plan ? nplan : (nframes + chunk - 1) / chunk;
   const size_t npix = (size_t)res * res;
-  Profiler prof(m, st);
-  int rc = VP_OK;
-  int ci = 0;
-  for (int t0 = 0; t0 < nframes && rc == VP_OK; t0 += chunk, ++ci) {
-    const int n = std::min(chunk, nframes - t0);
-    if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, nframes, group, st, prof);
-    if (rc != VP_OK) break;
-    rc = render_chunk(m, n, ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr,
-                      reinterpret_cast<const FrameParams*>(params_dev) + t0, rotate_shape_first, res,
-                      image_dev + (size_t)t0 * npix * 3, face_mask_dev ? face_mask_dev + (size_t)t0 * npix : nullptr,
-                      st, prof);
-    if (rc == VP_OK && notify_frames > 0) VP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(events[ci]), st));
+  ChunkRunner run(m, st);
+  int rc = run.init(nframes, res, chunk, nchunks, ex_dev, reinterpret_cast<const FrameParams*>(params_dev),
+                    rotate_shape_first);
+  int t0 = 0;
+  for (int ci = 0; ci < nchunks && rc == VP_OK; ++ci) {
+    int left = plan ? plan[ci] : std::min(chunk, nframes - t0);
+    bool on_main = false, on_aux = false;
+    while (left > 0 && rc == VP_OK) {  // more than one launch only when the chunk crosses a basis group
+      const int n = run.clip(t0, left);
+      cudaStream_t used = st;
+      rc = run.run(t0, n, image_dev + (size_t)t0 * npix * 3, face_mask_dev ? face_mask_dev + (size_t)t0 * npix : nullptr,
+                   &used);
+      (used == st ? on_main : on_aux) = true;
+      t0 += n;
+      left -= n;
+    }
+    if (rc == VP_OK && plan) {  // events[ci]: recorded where it covers every part of the chunk
+      if (on_aux && on_main) {
+        VP_CUDA(cudaEventRecord(m->ev_main_done, m->aux_stream));
+        VP_CUDA(cudaStreamWaitEvent(st, m->ev_main_done, 0));
+      }
+      VP_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(events[ci]), (on_aux && !on_main) ? m->aux_stream : st));
+    }
   }
-  if (rc != VP_OK) m->key_epoch = 0;
-  prof.finish();
-  return rc;
+  return run.finish(rc);
 }
 
 extern "C" int vp_render_sequence_dev(vp_model* m, int nframes, const float* ex_dev, const vp_frame_params* params_dev,
                                       int rotate_shape_first, int res, unsigned char* image_dev,
                                       unsigned char* face_mask_dev, void* stream) {
   return render_sequence_dev_impl(m, nframes, ex_dev, params_dev, rotate_shape_first, res, image_dev, face_mask_dev,
-                                  stream, 0, nullptr, 0);
+                                  stream, nullptr, 0, nullptr);
 }
 
 // Same, rendered in chunks of `notify_frames` frames with events[i] (cudaEvent_t) recorded on `stream`
@@ -193,8 +280,24 @@ extern "C" int vp_render_sequence_dev_notify(vp_model* m, int nframes, const flo
                                              unsigned char* image_dev, unsigned char* face_mask_dev, void* stream,
                                              int notify_frames, void** events, int nevents) {
   VP_REQUIRE(notify_frames > 0, "notify_frames must be positive");
+  VP_REQUIRE(nframes >= 0 && (nframes + notify_frames - 1) / notify_frames <= nevents, "not enough events for the chunks");
+  std::vector<int> plan;
+  for (int t0 = 0; t0 < nframes; t0 += notify_frames) plan.push_back(std::min(notify_frames, nframes - t0));
+  if (plan.empty()) return VP_OK;
   return render_sequence_dev_impl(m, nframes, ex_dev, params_dev, rotate_shape_first, res, image_dev, face_mask_dev,
-                                  stream, notify_frames, events, nevents);
+                                  stream, plan.data(), (int)plan.size(), events);
+}
+
+// Same with an explicit chunk plan: chunk_frames[i] frames in chunk i (they add up to nframes), events[i]
+// recorded when chunk i is complete.  Lets a caller whose consumer is the slow side (the NVLink ingest of
+// rank 0 in a multi-GPU gather) start it early with a short first chunk and end it with a short last one.
+extern "C" int vp_render_sequence_dev_chunks(vp_model* m, int nframes, const float* ex_dev,
+                                             const vp_frame_params* params_dev, int rotate_shape_first, int res,
+                                             unsigned char* image_dev, unsigned char* face_mask_dev, void* stream,
+                                             const int* chunk_frames, int nchunks, void** events) {
+  VP_REQUIRE(chunk_frames != nullptr && nchunks > 0 && events != nullptr, "bad chunk plan");
+  return render_sequence_dev_impl(m, nframes, ex_dev, params_dev, rotate_shape_first, res, image_dev, face_mask_dev,
+                                  stream, chunk_frames, nchunks, events);
 }
 
 extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, unsigned char* image,
@@ -246,60 +349,56 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
 
   const int chunk = chunk_frames(m, res, T, outputs_on_device == 0);
   const bool forced_chunk = env_size("VPB200_CHUNK_FRAMES", 0) != 0;
-  const int group = basis_group_frames(chunk, T);
-  VP_TRY(reserve_chunk(m, chunk, group, res));
   const size_t npix = (size_t)res * res;
-  Profiler prof(m, st);
-  int rc = VP_OK;
+  // The drain over PCIe (about 3.5 us per 256x256 frame) is the slow side of the host-output pipeline, so what
+  // matters is how soon it starts: the first chunk is short, the following ones full-sized.
+  const int first = (outputs_on_device || forced_chunk || T < 4 * 8) ? chunk : std::max(6, chunk / 3);
+  const int nchunks_est = 2 + (T + chunk - 1) / chunk + T / 96;
+  ChunkRunner run(m, st);
+  // host outputs: the PCIe drain is the slow side and wants the FIRST chunk as early as possible, which two
+  // chunks in flight delay (measured: 454 vs 417 us per 75-frame call), so that path stays on one stream
+  int rc = run.init(T, res, chunk, nchunks_est, ex_dev, params_dev, fr->rotate_shape_first, outputs_on_device != 0);
+  if (rc != VP_OK) return run.finish(rc);
   if (outputs_on_device) {
-    for (int t0 = 0; t0 < T && rc == VP_OK; t0 += chunk) {
-      const int n = std::min(chunk, T - t0);
-      if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, T, group, st, prof);
-      if (rc != VP_OK) break;
-      rc = render_chunk(m, n, ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr,
-                        params_dev + t0, fr->rotate_shape_first, res, image + (size_t)t0 * npix * 3,
-                        face_mask ? face_mask + (size_t)t0 * npix : nullptr, st, prof);
+    for (int t0 = 0, n = 0; t0 < T && rc == VP_OK; t0 += n) {
+      n = run.clip(t0, T - t0);
+      rc = run.run(t0, n, image + (size_t)t0 * npix * 3, face_mask ? face_mask + (size_t)t0 * npix : nullptr, nullptr);
     }
     // device outputs: asynchronous, ordered on `stream` like any other work the caller enqueues there
-  } else {
-    // double-buffered: chunk i renders while chunk i-1 drains to the host on the copy stream
-    for (int b = 0; b < 2; ++b) {
-      VP_CUDA(m->ws_img[b].reserve((size_t)chunk * npix * 3, m->device));
-      if (face_mask) VP_CUDA(m->ws_mask[b].reserve((size_t)chunk * npix, m->device));
-    }
-    // The drain over PCIe (about 3.5 us per 256x256 frame) is the slow side of this pipeline, so what matters
-    // is how soon it starts: the first chunk is short, the following ones full-sized.
-    const int first = (forced_chunk || T < 4 * 8) ? chunk : std::max(6, chunk / 3);
-    int ci = 0;
-    for (int t0 = 0, n = 0; t0 < T && rc == VP_OK; t0 += n, ++ci) {
-      n = std::min(t0 == 0 ? first : chunk, T - t0);
-      if (t0 / group != (t0 + n - 1) / group) n = (t0 / group + 1) * group - t0;  // chunks do not straddle basis groups
-      const int b = ci & 1;
-      if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(st, m->ev_copy[b], 0));
-      if (t0 % group == 0) rc = basis_group(m, ex_dev, t0, T, group, st, prof);
-      if (rc != VP_OK) break;
-      rc = render_chunk(m, n, ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr,
-                        params_dev + t0, fr->rotate_shape_first, res, m->ws_img[b].as<unsigned char>(),
-                        face_mask ? m->ws_mask[b].as<unsigned char>() : nullptr, st, prof);
-      if (rc != VP_OK) break;
-      VP_CUDA(cudaEventRecord(m->ev_render[b], st));
-      VP_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_render[b], 0));
-      VP_CUDA(cudaMemcpyAsync(image + (size_t)t0 * npix * 3, m->ws_img[b].ptr, (size_t)n * npix * 3,
-                              cudaMemcpyDeviceToHost, m->copy_stream));
-      if (face_mask)
-        VP_CUDA(cudaMemcpyAsync(face_mask + (size_t)t0 * npix, m->ws_mask[b].ptr, (size_t)n * npix,
-                                cudaMemcpyDeviceToHost, m->copy_stream));
-      VP_CUDA(cudaEventRecord(m->ev_copy[b], m->copy_stream));
-    }
-    cudaError_t e1 = cudaStreamSynchronize(st);
-    cudaError_t e2 = cudaStreamSynchronize(m->copy_stream);
-    if (rc == VP_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
-      set_error("stream synchronize failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-      rc = VP_ERR_CUDA;
-    }
+    return run.finish(rc);
   }
-  if (rc != VP_OK) m->key_epoch = 0;
-  prof.finish();
+  // host outputs, double-buffered: chunk i renders while chunk i-1 drains to the host on the copy stream
+  for (int b = 0; b < 2; ++b) {
+    VP_CUDA(m->ws_img[b].reserve((size_t)chunk * npix * 3, m->device));
+    if (face_mask) VP_CUDA(m->ws_mask[b].reserve((size_t)chunk * npix, m->device));
+  }
+  int ci = 0;
+  for (int t0 = 0, n = 0; t0 < T && rc == VP_OK; t0 += n, ++ci) {
+    n = run.clip(t0, std::min(t0 == 0 ? first : chunk, T - t0));
+    const int b = ci & 1;
+    // the staging image of chunk ci - 2 must have drained; the wait goes on the stream chunk ci will use, which
+    // is the one chunk ci - 2 used (chunks alternate), or the only one
+    cudaStream_t cs = (run.dual && (run.issued & 1)) ? m->aux_stream : st;
+    if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(cs, m->ev_copy[b], 0));
+    cudaStream_t used = st;
+    rc = run.run(t0, n, m->ws_img[b].as<unsigned char>(), face_mask ? m->ws_mask[b].as<unsigned char>() : nullptr, &used);
+    if (rc != VP_OK) break;
+    VP_CUDA(cudaEventRecord(m->ev_render[b], used));
+    VP_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_render[b], 0));
+    VP_CUDA(cudaMemcpyAsync(image + (size_t)t0 * npix * 3, m->ws_img[b].ptr, (size_t)n * npix * 3, cudaMemcpyDeviceToHost,
+                            m->copy_stream));
+    if (face_mask)
+      VP_CUDA(cudaMemcpyAsync(face_mask + (size_t)t0 * npix, m->ws_mask[b].ptr, (size_t)n * npix, cudaMemcpyDeviceToHost,
+                              m->copy_stream));
+    VP_CUDA(cudaEventRecord(m->ev_copy[b], m->copy_stream));
+  }
+  rc = run.finish(rc);
+  cudaError_t e1 = cudaStreamSynchronize(st);
+  cudaError_t e2 = cudaStreamSynchronize(m->copy_stream);
+  if (rc == VP_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+    set_error("stream synchronize failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    rc = VP_ERR_CUDA;
+  }
   return rc;
 }
 

@@ -117,10 +117,10 @@ def device_inputs(coeffs, angles, device):
   return ex_dev, params_dev
 
 
-def render_device(dm, ex_dev, params_dev, rotate_first, res, out, mask=None, notify_frames=0):
-  """vp_render_sequence_dev(_notify) on torch CUDA tensors, asynchronous on the current stream.
-  With notify_frames > 0 returns one torch event per chunk of that many frames, recorded when the
-  chunk's frames are complete."""
+def render_device(dm, ex_dev, params_dev, rotate_first, res, out, mask=None, notify_frames=0, plan=None):
+  """vp_render_sequence_dev(_notify / _chunks) on torch CUDA tensors, asynchronous on the current stream.
+  With notify_frames > 0 (uniform chunks) or plan = [n0, n1, ...] (explicit chunk sizes adding up to T)
+  returns one torch event per chunk, recorded when the chunk's frames are complete."""
   import ctypes
   import torch
   from . import _lib
@@ -128,19 +128,43 @@ def render_device(dm, ex_dev, params_dev, rotate_first, res, out, mask=None, not
   stream = ctypes.c_void_p(torch.cuda.current_stream(ex_dev.device).cuda_stream)
   mask_ptr = None if mask is None else ctypes.c_void_p(mask.data_ptr())
   out_ptr = ctypes.c_void_p(out if isinstance(out, int) else out.data_ptr())   # int: a (peer) device address
-  if notify_frames <= 0:
+  if plan is None and notify_frames > 0:
+    plan = [min(notify_frames, t - a) for a in range(0, t, notify_frames)]
+  if not plan:
     _lib.check(_lib.lib().vp_render_sequence_dev(dm.handle, t, ex_dev.data_ptr(), params_dev.data_ptr(),
                                                  int(bool(rotate_first)), res, out_ptr, mask_ptr, stream))
     return []
-  n_events = -(-t // notify_frames)
+  if sum(plan) != t or min(plan) <= 0:
+    raise ValueError('chunk plan %r does not add up to %d frames' % (plan, t))
+  n_events = len(plan)
   events = [torch.cuda.Event() for _ in range(n_events)]
   for ev in events:
     ev.record()                      # materialises the underlying cudaEvent_t
   handles = (ctypes.c_void_p * n_events)(*[ev.cuda_event for ev in events])
-  _lib.check(_lib.lib().vp_render_sequence_dev_notify(dm.handle, t, ex_dev.data_ptr(), params_dev.data_ptr(),
+  sizes = (ctypes.c_int * n_events)(*plan)
+  _lib.check(_lib.lib().vp_render_sequence_dev_chunks(dm.handle, t, ex_dev.data_ptr(), params_dev.data_ptr(),
                                                       int(bool(rotate_first)), res, out_ptr, mask_ptr, stream,
-                                                      notify_frames, handles, n_events))
+                                                      sizes, n_events, handles))
   return events
+
+
+def push_plan(n_local, world):
+  """Chunk sizes for the push gather.  Rank 0's NVLink ingest ((world - 1) frames per rendered frame) is as
+  slow as the rendering itself from 8 ranks on, so the step costs about first chunk + all pushes, or all
+  renders + last push, whichever is larger: a short first and a short last chunk around large middle ones."""
+  import os
+  env = os.environ.get('VPB200_PUSH_PLAN')
+  if env:
+    plan = [int(x) for x in env.split(',') if x]
+    if sum(plan) == n_local:
+      return plan
+  if n_local < 48:
+    return [n_local]
+  edge = max(8, n_local // 8)
+  mid = n_local - 2 * edge
+  n_mid = max(1, -(-mid // 192)) if world <= 4 else max(2, -(-mid // 96))
+  base, extra = divmod(mid, n_mid)
+  return [edge] + [base + (1 if i < extra else 0) for i in range(n_mid)] + [edge]
 
 
 def gather_notify_frames(n_local, world):
@@ -260,19 +284,19 @@ class PeerFrameBuffer(object):
     else:
       if self.local is None:
         self.local = torch.empty((self.per, self.res, self.res, 3), dtype=torch.uint8, device=self.device)
-      if notify_frames is None:
-        notify_frames = n if n < 48 else -(-n // 3)
+      plan = push_plan(n, self.world) if notify_frames is None else [min(notify_frames, n - a) for a in range(0, n, notify_frames)]
       copy = _comm_stream(self.device)
       sstream = ctypes.c_void_p(copy.cuda_stream)
       if n > 0:
-        events = render_device(dm, ex_dev, params_dev, rotate_first, self.res, self.local, notify_frames=notify_frames)
+        events = render_device(dm, ex_dev, params_dev, rotate_first, self.res, self.local, plan=plan)
+        a = 0
         for c, ev in enumerate(events):
-          a = c * notify_frames
-          b = min(n, a + notify_frames)
+          b = a + plan[c]
           copy.wait_event(ev)
           _lib.check(lib.vp_copy_async(ctypes.c_void_p(self.slice_ptr + a * self.frame_bytes),
                                        ctypes.c_void_p(self.local.data_ptr() + a * self.frame_bytes),
                                        (b - a) * self.frame_bytes, sstream))
+          a = b
       else:
         copy.wait_stream(compute)
       _lib.check(lib.vp_peer_signal(flag, self.step, sstream))

@@ -89,7 +89,13 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
     a.frames_per_block = fpb;
     a.h = h;
     a.w = w;
-    raster_scatter_packed_kernel<<<grid, kRasterBlock, 0, st>>>(a);
+    static const int minb = [] { const char* e = std::getenv("VPB200_SCATTER_MINB"); return e ? std::atoi(e) : 5; }();  // 48 registers, 40 warps/SM: +3 % over 64 / 32
+    if (minb >= 6)
+      raster_scatter_packed_kernel<6><<<grid, kRasterBlock, 0, st>>>(a);
+    else if (minb == 5)
+      raster_scatter_packed_kernel<5><<<grid, kRasterBlock, 0, st>>>(a);
+    else
+      raster_scatter_packed_kernel<4><<<grid, kRasterBlock, 0, st>>>(a);
   }
   VP_LAUNCH_CHECK();
   return VP_OK;

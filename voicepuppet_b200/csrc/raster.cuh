@@ -225,7 +225,8 @@ __device__ __forceinline__ uint32_t flat_color_packed(uint32_t a, uint32_t b, ui
   return r3 | g3 | b3 | 0xFF000000u;
 }
 
-__global__ void __launch_bounds__(kRasterBlock)
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kRasterBlock, MIN_BLOCKS)
 raster_scatter_packed_kernel(const ScatterArgs a) {
   __shared__ Candidate s_big[kRasterBlock / 32];
   const int f = blockIdx.x * kRasterBlock + threadIdx.x;

@@ -368,6 +368,8 @@ struct LocalVerts {
     for (int q = 0; q < kSlotsV; ++q)
       if (q < nq_v) pos[tid + q * kTileV] = make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
   }
+  // the staged position of the thread's first local vertex (its own vertex), kept in registers by the fan kernel
+  __device__ __forceinline__ float3 own_staged() const { return make_float3(rx[0] + dx[0], ry[0] + dy[0], rz[0] + dz[0]); }
 };
 
 __device__ __forceinline__ void stage_frame_constants(const VertexArgs& a, FrameShared* dst, int f, int tid) {
@@ -410,6 +412,7 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const Ve
   lv.fetch(a, f_begin, nq_v);
   stage_frame_constants(a, &s_frame[0], f_begin, tid);
   lv.stage(s_pos[0], tid, nq_v);
+  float3 pv = lv.own_staged();                           // == s_pos[buf][tid], without the shared-memory read
   float d0x = lv.dx[0], d0y = lv.dy[0], d0z = lv.dz[0];  // own displacement of the frame being finished
   if (f_begin + 1 < f_end) lv.fetch(a, f_begin + 1, nq_v);
   __syncthreads();
@@ -418,7 +421,6 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const Ve
     const int buf = (f - f_begin) & 1;
     if (own) {
       const char* pos = reinterpret_cast<const char*>(s_pos[buf]);
-      const float4 pv = s_pos[buf][tid];
       float nx = 0.f, ny = 0.f, nz = 0.f;
       float4 p = *reinterpret_cast<const float4*>(pos + (fan[0] & 0xFFFFu));
       float ex = p.x - pv.x, ey = p.y - pv.y, ez = p.z - pv.z;
@@ -446,6 +448,7 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const Ve
     if (f + 1 < f_end) {
       stage_frame_constants(a, &s_frame[buf ^ 1], f + 1, tid);
       lv.stage(s_pos[buf ^ 1], tid, nq_v);
+      pv = lv.own_staged();
       d0x = lv.dx[0];
       d0y = lv.dy[0];
       d0z = lv.dz[0];

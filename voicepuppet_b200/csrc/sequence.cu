@@ -36,7 +36,10 @@ int chunk_frames(const vp_model* m, int res, int nframes, bool host_outputs) {
   const size_t t = (size_t)std::max(nframes, 1);
   if (forced) return (int)std::min(c, t);
   if (host_outputs) c = std::min(c, std::max<size_t>(8, (t + 3) / 4));
-  const size_t nchunks = std::max<size_t>(1, (t * 10 + c * 11 - 1) / (c * 11));  // ceil(t / (1.1 c))
+  size_t nchunks = std::max<size_t>(1, (t * 10 + c * 11 - 1) / (c * 11));  // ceil(t / (1.1 c))
+  // two chunks on the two streams of ChunkRunner beat one large launch sequence (75 frames at 256x256: 149 vs
+  // 156 us): the second chunk's kernels fill the tails of the first's
+  if (!host_outputs && nchunks == 1 && t >= 48 && !m->profiling) nchunks = 2;  // per-kernel profiling times whole launches
   return (int)((t + nchunks - 1) / nchunks);
 }
 

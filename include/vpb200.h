@@ -174,6 +174,19 @@ int vp_composite_dev(const unsigned char* frames_dev, int nframes, int res, int 
                      int canvas_h, int canvas_w, unsigned char* canvas_dev, int swap_rb, float* inputs_dev,
                      int in_channels, int channel_offset, int device, void* stream);
 
+/* Training-time twin (voicepuppet/bfmnet/bfmnet.py:215-268, BFMNet's vertex loss): with Delta = ex_label - ex_pred
+ * and D = exBase . Delta,
+ *   loss = 1/B sum_{b,t<len_b} sum_r M_r |D[b,t,r]|  +  1/B sum_{b,t<len_b-1} sum_r M_r |D[b,t,r] - D[b,t+1,r]|
+ * (identity and mean cancel in the reference's face_shape - output_face_shape), and its gradient with respect to
+ * Delta (= minus the gradient with respect to the predicted coefficients).
+ * vp_loss_mask_create: mask[nver*3] f32 in the model's vertex order (the reference's mouth_mask, :134-137) -> device
+ * array in the library's row order.  vp_expression_loss_dev: delta_ex_dev[batch*frames][64], seq_len_dev[batch] i32,
+ * loss_dev one double, grad_delta_dev[batch*frames][64] (NULL = forward only); device pointers, asynchronous. */
+int vp_loss_mask_create(vp_model* m, const float* mask_host, float** mask_dev);
+void vp_loss_mask_destroy(float* mask_dev);
+int vp_expression_loss_dev(vp_model* m, const float* delta_ex_dev, const int* seq_len_dev, const float* mask_dev,
+                           int batch, int frames, double* loss_dev, float* grad_delta_dev, void* stream);
+
 /* Expression-basis kernel selection: 0 = automatic (FP32 streamed kernel below 16 frames per launch,
  * tcgen05 3xTF32 GEMM from 16 frames up), 1 = always FP32 SIMT, 2 = always tcgen05 3xTF32. */
 int vp_set_basis_mode(vp_model* m, int mode);

@@ -95,6 +95,9 @@ SIGNATURES = {
     'vp_render_sequence_dev_notify': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _i]),
     'vp_render_sequence_dev_chunks': (_i, [_vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     'vp_basis_dev': (_i, [_vp, _vp, _vp, _i, _vp]),
+    'vp_loss_mask_create': (_i, [_vp, _vp, ctypes.POINTER(_vp)]),
+    'vp_loss_mask_destroy': (None, [_vp]),
+    'vp_expression_loss_dev': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     'vp_model_rows_pad': (_i, [_vp]),
     'vp_debug_basis_trace': (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     'vp_launch_count': (ctypes.c_ulonglong, []),

@@ -50,7 +50,7 @@ def test_loss_and_gradient_small_model(small_model, b, t):
   p = torch.tensor(pred, device='cuda:0', requires_grad=True)
   lab = torch.tensor(coeffs[:, :, 80:144], device='cuda:0')
   loss = loss_fn(p, lab, seq_len)
-  assert abs(float(loss) - want) <= 1e-5 * abs(want), (float(loss), want)
+  assert abs(float(loss.detach()) - want) <= 1e-5 * abs(want), (float(loss.detach()), want)
   loss.backward()
   got = p.grad.cpu().numpy().astype(np.float64)
   ref = analytic_grad(pred, coeffs, seq_len, small_model, mask)
@@ -81,7 +81,7 @@ def test_loss_full_model_matches_oracle_and_is_deterministic(full_model):
     p = torch.tensor(pred, device='cuda:0', requires_grad=True)
     loss = loss_fn(p, lab, seq_len)
     loss.backward()
-    outs.append((float(loss), p.grad.cpu().numpy()))
+    outs.append((float(loss.detach()), p.grad.cpu().numpy()))
   assert abs(outs[0][0] - want) <= 1e-5 * abs(want), (outs[0][0], want)
   assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])       # fixed reduction order
   ref = analytic_grad(pred, coeffs, seq_len, full_model, mask)

@@ -159,7 +159,8 @@ constexpr int kBasisTensorMinFrames = 16;  // below this the frame batch is a GE
 int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes,
                   int rotate_first, double focal, double center, double image_size, double raster_scale,
                   float4* vrec_dev, const ReconOut& out, cudaStream_t st, const void* frame_constants = nullptr);
-int prepare_frame_constants(vp_model* m, const FrameParams* params_dev, int nframes, cudaStream_t st, const void** out);
+int prepare_frame_constants(vp_model* m, const FrameParams* params_dev, int nframes, int rotate_first, double focal,
+                            double center, double image_size, double raster_scale, cudaStream_t st, const void** out);
 size_t frame_constants_stride();
 
 }  // namespace vp

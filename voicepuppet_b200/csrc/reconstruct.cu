@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "launch.h"
@@ -186,6 +187,24 @@ struct __align__(16) FrameShared {   // per-frame constants staged in shared mem
   float sh[28];        // gamma with the SH band constants (and the 0.8 ambient) folded in: [3][9]
 };
 
+// The same frame folded further, for the raster-record-only path (no per-vertex outputs requested):
+//  * geometry: rotation(s), translation, camera, focal / centre, the y flip and the raster scale are one
+//    projective map of the unrotated vertex v (float64): X = v.ax + bx, Y = v.ay + by, zc = v.az + bz,
+//    record = (X / zc, Y / zc, -zc)   [Reconstruction_rotation :211 + Projection_layer :100-120 + :215 + the
+//    xy * res/224 convention]
+//  * lighting: rotating the normal and evaluating the 9 SH bands is a quadratic form of the UNROTATED unit
+//    normal n per channel: lit = c + b.n + n'Qn with b = R b_r, Q = R Q_r R' (Illumination_layer :129-168)
+struct __align__(16) FrameFast {
+  double lin[12];      // ax[3], bx, ay[3], by, az[3], bz
+  float shq[32];       // per channel 10 values: c, bx, by, bz, qxx, qyy, qzz, 2qxy, 2qxz, 2qyz (30 used)
+};
+
+struct __align__(16) FrameConst {
+  FrameShared slow;
+  FrameFast fast;
+};
+static_assert(sizeof(FrameFast) == 224 && sizeof(FrameConst) == 576, "frame constant layout");
+
 struct VertexArgs {
   const TileDesc* tiles;
   const int* tile_list;        // blockIdx.x -> tile id (this launch's slice of vp_model::tile_list)
@@ -198,7 +217,7 @@ struct VertexArgs {
   const float* tex;
   const float* disp;
   size_t disp_stride;
-  const FrameShared* fshared;  // per-frame constants prepared by frame_prep_kernel
+  const FrameConst* fshared;   // per-frame constants prepared by frame_prep_kernel
   int nframes;
   int frames_per_block;
   int rotate_first;
@@ -217,27 +236,113 @@ static_assert(sizeof(FrameShared) == 352, "FrameShared layout");
 // the SH coefficients with the band constants folded in (Illumination_layer, reconstruct_mesh.py:133-153:
 // Y_k = K_k * b_k(n), lit_c = sum_k Y_k gamma'_ck with gamma' = gamma + 0.8 on band 0; K_k are products
 // of a0..a2 and c0..c2 evaluated in float64).
-__global__ void frame_prep_kernel(const FrameParams* __restrict__ params, FrameShared* __restrict__ out, int nframes) {
+__global__ void frame_prep_kernel(const FrameParams* __restrict__ params, FrameConst* __restrict__ out_all, int nframes,
+                                  int rotate_first, double focal, double center, double image_size, double scale) {
   const int f = blockIdx.x * (blockDim.x / 64) + threadIdx.x / 64;
   const int t = threadIdx.x % 64;
   if (f >= nframes) return;
   const FrameParams& p = params[f];
-  FrameShared& o = out[f];
+  FrameShared& o = out_all[f].slow;
   if (t < 48) reinterpret_cast<uint32_t*>(&o.par)[t] = reinterpret_cast<const uint32_t*>(&p)[t];
   if (t < 12) o.rot[t] = t < 9 ? (float)p.rot[t] : 0.f;
+  auto band_constant = [](int k) {
+    return (k == 0) ? 0.8862269254527579
+                    : (k <= 3 ? 1.772453850905516
+                              : (k == 6 ? 0.7006239020497412 : (k == 8 ? 1.2135161953473121 : 2.4270323906946243)));
+  };
+  auto folded = [&](int c, int k) {  // sign * K_k * (gamma_ck + 0.8 [k == 0])
+    const double sign = (k == 1 || k == 3 || k == 5 || k == 7) ? -1.0 : 1.0;
+    return sign * band_constant(k) * (double)(p.gamma[9 * c + k] + (k == 0 ? 0.8f : 0.f));  // float32 add, like numpy's in-place += 0.8
+  };
   if (t >= 32 && t < 60) {
     const int i = t - 32;
     if (i >= 27) {
       o.sh[i] = 0.f;
     } else {
       const int k = i % 9;
-      const float kk = (k == 0) ? 0.8862269254527579f
-                                : (k <= 3 ? 1.772453850905516f
-                                          : (k == 6 ? 0.7006239020497412f : (k == 8 ? 1.2135161953473121f : 2.4270323906946243f)));
+      const float kk = (float)band_constant(k);
       const float sign = (k == 1 || k == 3 || k == 5 || k == 7) ? -1.f : 1.f;
       o.sh[i] = sign * kk * (p.gamma[i] + (k == 0 ? 0.8f : 0.f));
     }
   }
+  FrameFast& q = out_all[f].fast;
+  if (t == 60) {  // the projective map, float64
+    const double* R = p.rot;
+    double M[9];
+    if (rotate_first) {
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) M[3 * i + j] = R[3 * i] * R[j] + R[3 * i + 1] * R[3 + j] + R[3 * i + 2] * R[6 + j];
+    } else {
+      for (int i = 0; i < 9; ++i) M[i] = R[i];
+    }
+    const double t0 = (double)p.trans[0], t1 = (double)p.trans[1], t2 = (double)p.trans[2];
+    const double bz = 10.0 - t2;
+    const double bx = focal * t0 + center * bz, by = focal * t1 + center * bz;
+    for (int i = 0; i < 3; ++i) {
+      const double az = -M[3 * i + 2];
+      const double ax = focal * M[3 * i] + center * az, ay = focal * M[3 * i + 1] + center * az;
+      q.lin[i] = scale * ax;
+      q.lin[4 + i] = scale * (image_size * az - ay);
+      q.lin[8 + i] = az;
+    }
+    q.lin[3] = scale * bx;
+    q.lin[7] = scale * (image_size * bz - by);
+    q.lin[11] = bz;
+  }
+  if (t >= 61 && t < 64) {  // one colour channel each: the quadratic form of the unrotated normal
+    const int c = t - 61;
+    const double* R = p.rot;  // n_r = n R  (row vector), so b = R b_r and Q = R Q_r R'
+    double g[9];
+    for (int k = 0; k < 9; ++k) g[k] = folded(c, k);
+    const double br[3] = {g[3], g[1], g[2]};
+    const double Qr[9] = {g[8], 0.5 * g[4], 0.5 * g[7], 0.5 * g[4], -g[8], 0.5 * g[5], 0.5 * g[7], 0.5 * g[5], 3.0 * g[6]};
+    double b[3], RQ[9], Q[9];
+    for (int i = 0; i < 3; ++i) b[i] = R[3 * i] * br[0] + R[3 * i + 1] * br[1] + R[3 * i + 2] * br[2];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) RQ[3 * i + j] = R[3 * i] * Qr[j] + R[3 * i + 1] * Qr[3 + j] + R[3 * i + 2] * Qr[6 + j];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Q[3 * i + j] = RQ[3 * i] * R[3 * j] + RQ[3 * i + 1] * R[3 * j + 1] + RQ[3 * i + 2] * R[3 * j + 2];
+    float* o10 = q.shq + 10 * c;
+    o10[0] = (float)(g[0] - g[6]);
+    o10[1] = (float)b[0];
+    o10[2] = (float)b[1];
+    o10[3] = (float)b[2];
+    o10[4] = (float)Q[0];
+    o10[5] = (float)Q[4];
+    o10[6] = (float)Q[8];
+    o10[7] = (float)(2.0 * Q[1]);
+    o10[8] = (float)(2.0 * Q[2]);
+    o10[9] = (float)(2.0 * Q[5]);
+    if (c == 0) q.shq[30] = q.shq[31] = 0.f;
+  }
+}
+
+// The raster-record-only finish (see FrameFast): 6 + 27 float32 operations for the lighting, 9 DFMA + one
+// reciprocal + 2 DMUL for the geometry.
+__device__ __forceinline__ void finish_vertex_fast(const VertexArgs& a, const FrameFast& ff, int f, int gv0, float nx,
+                                                   float ny, float nz, float tr, float tg, float tb, double vx,
+                                                   double vy, double vz) {
+  {
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz);  // 0 * inf -> NaN for a vertex without faces
+    nx *= inv;
+    ny *= inv;
+    nz *= inv;
+  }
+  const float xx = nx * nx, yy = ny * ny, zz = nz * nz, xy = nx * ny, xz = nx * nz, yz = ny * nz;
+  float lit[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* g = ff.shq + 10 * c;
+    lit[c] = g[0] + g[1] * nx + g[2] * ny + g[3] * nz + g[4] * xx + g[5] * yy + g[6] * zz + g[7] * xy + g[8] * xz + g[9] * yz;
+  }
+  const float cr = lit[0] * tr, cg = lit[1] * tg, cb = lit[2] * tb;
+  const double* L = ff.lin;
+  const double X = vx * L[0] + vy * L[1] + vz * L[2] + L[3];
+  const double Y = vx * L[4] + vy * L[5] + vz * L[6] + L[7];
+  const double zc = vx * L[8] + vy * L[9] + vz * L[10] + L[11];
+  const double inv = 1.0 / zc;
+  const uint32_t rgba = clip_trunc_byte(cr) | (clip_trunc_byte(cg) << 8) | (clip_trunc_byte(cb) << 16);
+  a.vrec[(size_t)f * a.vrec_stride + gv0] = make_float4((float)(X * inv), (float)(Y * inv), (float)(-zc), __uint_as_float(rgba));
 }
 
 // What both vertex kernels do once the summed face normal (nx, ny, nz) of the own vertex is known:
@@ -374,17 +479,22 @@ struct LocalVerts {
 
 __device__ __forceinline__ void stage_frame_constants(const VertexArgs& a, FrameShared* dst, int f, int tid) {
   if (tid < (int)(sizeof(FrameShared) / 4))
-    reinterpret_cast<uint32_t*>(dst)[tid] = __ldg(reinterpret_cast<const uint32_t*>(a.fshared + f) + tid);
+    reinterpret_cast<uint32_t*>(dst)[tid] = __ldg(reinterpret_cast<const uint32_t*>(&a.fshared[f].slow) + tid);
+}
+__device__ __forceinline__ void stage_frame_constants(const VertexArgs& a, FrameFast* dst, int f, int tid) {
+  if (tid < (int)(sizeof(FrameFast) / 4))
+    reinterpret_cast<uint32_t*>(dst)[tid] = __ldg(reinterpret_cast<const uint32_t*>(&a.fshared[f].fast) + tid);
 }
 
 // K2, fan flavour (tiles whose vertices all have fan records: any manifold mesh).  One CTA per (tile,
 // run of frames).  Per frame: the own vertex sums (u_i - v) x (u_i+1 - v) over its ring from 9 gathers of
 // staged positions, finishes (finish_vertex), stages the next frame's positions into the other buffer,
 // and the block synchronises once.  Shared memory holds positions only (no per-triangle pass).
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool FAST>
 __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const VertexArgs a) {
+  using Frame = typename std::conditional<FAST, FrameFast, FrameShared>::type;
   __shared__ float4 s_pos[2][kTileLV];
-  __shared__ __align__(16) FrameShared s_frame[2];
+  __shared__ __align__(16) Frame s_frame[2];
 
   const TileDesc td = a.tiles[__ldg(a.tile_list + blockIdx.x)];
   const int tid = threadIdx.x;
@@ -439,10 +549,15 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const Ve
         ey = gy;
         ez = gz;
       }
-      int orig = 0;
-      if (a.has_out) orig = __ldg(a.v_int2orig + lv.gv[0]);
-      finish_vertex(a, s_frame[buf], f, lv.gv[0], orig, nx, ny, nz, tr, tg, tb, lv.bx + (double)d0x,
-                    lv.by + (double)d0y, lv.bz + (double)d0z);
+      if constexpr (FAST) {
+        finish_vertex_fast(a, s_frame[buf], f, lv.gv[0], nx, ny, nz, tr, tg, tb, lv.bx + (double)d0x,
+                           lv.by + (double)d0y, lv.bz + (double)d0z);
+      } else {
+        int orig = 0;
+        if (a.has_out) orig = __ldg(a.v_int2orig + lv.gv[0]);
+        finish_vertex(a, s_frame[buf], f, lv.gv[0], orig, nx, ny, nz, tr, tg, tb, lv.bx + (double)d0x,
+                      lv.by + (double)d0y, lv.bz + (double)d0z);
+      }
     }
     // ---- stage frame f + 1 into the other buffers (their readers passed the previous barrier) ----
     if (f + 1 < f_end) {
@@ -547,17 +662,19 @@ __global__ void __launch_bounds__(kTileV, 5) vertex_tile_kernel(const VertexArgs
 
 // Per-frame constants of `nframes` frames into m->ws_fshared (one launch per sequence); the returned pointer,
 // advanced by frame_constants_stride() per frame, is what launch_vertex takes as `frame_constants`.
-int prepare_frame_constants(vp_model* m, const FrameParams* params_dev, int nframes, cudaStream_t st, const void** out) {
+int prepare_frame_constants(vp_model* m, const FrameParams* params_dev, int nframes, int rotate_first, double focal,
+                            double center, double image_size, double raster_scale, cudaStream_t st, const void** out) {
   *out = nullptr;
   if (nframes == 0) return VP_OK;
-  VP_CUDA(m->ws_fshared.reserve((size_t)nframes * sizeof(FrameShared), m->device));
-  FrameShared* fshared = m->ws_fshared.as<FrameShared>();
-  frame_prep_kernel<<<(nframes + 3) / 4, 256, 0, st>>>(params_dev, fshared, nframes);
+  VP_CUDA(m->ws_fshared.reserve((size_t)nframes * sizeof(FrameConst), m->device));
+  FrameConst* fc = m->ws_fshared.as<FrameConst>();
+  frame_prep_kernel<<<(nframes + 3) / 4, 256, 0, st>>>(params_dev, fc, nframes, rotate_first, focal, center, image_size,
+                                                      raster_scale);
   VP_LAUNCH_CHECK();
-  *out = fshared;
+  *out = fc;
   return VP_OK;
 }
-size_t frame_constants_stride() { return sizeof(FrameShared); }
+size_t frame_constants_stride() { return sizeof(FrameConst); }
 
 int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_dev, int nframes, int rotate_first,
                   double focal, double center, double image_size, double raster_scale, float4* vrec_dev,
@@ -576,8 +693,10 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.disp = disp_dev;
   a.disp_stride = (size_t)m->rows_pad;
   const void* prepared = frame_constants;
-  if (prepared == nullptr) VP_TRY(prepare_frame_constants(m, params_dev, nframes, st, &prepared));
-  a.fshared = static_cast<const FrameShared*>(prepared);
+  if (prepared == nullptr)
+    VP_TRY(prepare_frame_constants(m, params_dev, nframes, rotate_first, focal, center, image_size, raster_scale, st,
+                                   &prepared));
+  a.fshared = static_cast<const FrameConst*>(prepared);
   a.nframes = nframes;
   a.rotate_first = rotate_first;
   a.has_out = (out.shape || out.norm || out.color || out.proj || out.zbuf) ? 1 : 0;
@@ -606,12 +725,18 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
     const int minb = minb_env > 0 ? minb_env : 8;
     a.frames_per_block = frames_per_block(n_fan, minb, 2);
     dim3 grid(n_fan, (nframes + a.frames_per_block - 1) / a.frames_per_block);
-    if (minb <= 6)
-      vertex_fan_kernel<6><<<grid, kTileV, 0, st>>>(a);
-    else if (minb == 7)
-      vertex_fan_kernel<7><<<grid, kTileV, 0, st>>>(a);
-    else
-      vertex_fan_kernel<8><<<grid, kTileV, 0, st>>>(a);
+    static const int slow_env = [] { const char* e = std::getenv("VPB200_VERTEX_SLOW"); return e ? std::atoi(e) : 0; }();
+    const bool fast = !a.has_out && a.vrec != nullptr && !slow_env;  // raster records only: the folded constants
+    if (fast) {
+      if (minb <= 6)
+        vertex_fan_kernel<6, true><<<grid, kTileV, 0, st>>>(a);
+      else if (minb == 7)
+        vertex_fan_kernel<7, true><<<grid, kTileV, 0, st>>>(a);
+      else
+        vertex_fan_kernel<8, true><<<grid, kTileV, 0, st>>>(a);
+    } else {
+      vertex_fan_kernel<6, false><<<grid, kTileV, 0, st>>>(a);
+    }
     VP_LAUNCH_CHECK();
   }
   if (m->ntiles - n_fan > 0) {

@@ -130,7 +130,7 @@ struct ChunkRunner {
       m->key_epoch = 0;
     }
     const void* fc = nullptr;
-    VP_TRY(prepare_frame_constants(m, params_dev, nframes, st, &fc));
+    VP_TRY(prepare_frame_constants(m, params_dev, nframes, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, st, &fc));
     fconst = static_cast<const char*>(fc);
     if (dual) VP_CUDA(cudaEventRecord(m->ev_fork, st));
     return VP_OK;

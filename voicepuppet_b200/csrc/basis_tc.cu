@@ -94,7 +94,7 @@ __device__ __forceinline__ bool elect_one() {
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ ex, float* __restrict__ disp,
-                int nframes, int rows_pad, int ntiles, long long* __restrict__ trace) {
+                int nframes, int rows_pad, int ntiles, long long* __restrict__ trace, int store_policy) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // optional per-role timeline of CTA 0 (diagnostics): trace[role * 64 + it * 4 + k] = clock64()
   const bool tracing = trace != nullptr && blockIdx.x == 0;
@@ -248,8 +248,13 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
         ptx::tmem_ld_wait();
         float* o = out + (size_t)c0 * rows_pad;
         if (c0 + 16 <= nframes) {
+          if (store_policy == 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
+          } else {  // default policy: the displacements stay in L2 for the vertex kernel that reads them next
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[(size_t)j * rows_pad] = __uint_as_float(r[j]);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -355,11 +360,12 @@ int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nfram
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   const int grid = std::min(ntiles, sms);
+  static const int store_policy = [] { const char* e = std::getenv("VPB200_BASIS_STORE"); return e ? std::atoi(e) : 0; }();
   for (int t0 = 0; t0 < nframes; t0 += kTcN) {
     const int n = std::min(kTcN, nframes - t0);
     basis_tc_kernel<<<grid, kTcThreads, tc_smem_bytes((n + 15) & ~15), st>>>(map, ex_dev + (size_t)t0 * VP_N_EX,
                                                        disp_dev + (size_t)t0 * m->rows_pad, n, m->rows_pad, ntiles,
-                                                       trace_dev);
+                                                       trace_dev, store_policy);
     VP_LAUNCH_CHECK();
   }
   return VP_OK;

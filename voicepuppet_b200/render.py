@@ -277,9 +277,12 @@ class PeerFrameBuffer(object):
     compute = torch.cuda.current_stream(self.device)
     cstream = ctypes.c_void_p(compute.cuda_stream)
     flag = ctypes.c_void_p(self.flags_ptr + 4 * self.rank)
-    if self.rank == 0 or mode == 'store':
+    if self.rank == 0 or mode in ('store', 'store-chunks'):
       if n > 0:
-        render_device(dm, ex_dev, params_dev, rotate_first, self.res, int(self.slice_ptr))
+        # 'store-chunks': the same direct stores, cut into the push plan's chunks on the two streams of the
+        # chunk pipeline, so that one chunk's resolve kernel waits on NVLink while the next chunk computes
+        plan = push_plan(n, self.world) if (mode == 'store-chunks' and self.rank != 0) else None
+        render_device(dm, ex_dev, params_dev, rotate_first, self.res, int(self.slice_ptr), plan=plan)
       _lib.check(lib.vp_peer_signal(flag, self.step, cstream))
     else:
       if self.local is None:

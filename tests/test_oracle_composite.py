@@ -45,3 +45,18 @@ def test_paste_outside_the_canvas_raises_like_numpy():
   raster = np.zeros((224, 224, 3), np.uint8)
   with pytest.raises(ValueError):
     oc.composite(raster, 500, 256, 1.0, np.array([512, 512, 1.0, 0, 0.0]), (512, 512))
+
+
+def test_c_abi_placement_matches_the_reference_lines():
+  """vp_composite_placement (host only, no GPU): infer_bfmvid.py:80-82,112-121 -- Python's int() truncation
+  and round-half-even -- against the oracle on random parameters, including exact .5 sizes."""
+  from voicepuppet_b200 import render
+  rng = np.random.Generator(np.random.PCG64(9))
+  cases = [(256, 250, 1.05, [512, 512, 0.97, 12.3, -20.7]), (100, 100, 224 / 150.5, [0, 0, 1.0, 0.0, 0.0]),
+           (100, 100, 224 / 151.5, [0, 0, 1.0, -0.49, 0.51])]
+  for _ in range(200):
+    cases.append((int(rng.integers(0, 600)), int(rng.integers(0, 600)), float(rng.uniform(0.4, 2.5)),
+                  [512, 512, float(rng.uniform(0.7, 1.4)), float(rng.uniform(-60, 60)), float(rng.uniform(-60, 60))]))
+  for cx, cy, ratio, tp in cases:
+    for res in (224, 256):
+      assert render.composite_placement(cx, cy, ratio, tp, res) == oc.placement(cx, cy, ratio, np.array(tp), res), (cx, cy, ratio, tp, res)

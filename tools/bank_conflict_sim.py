@@ -49,6 +49,60 @@ def excess_wavefronts(tiles, fan):
   return total, ideal, by_entry
 
 
+def colouring_potential(tiles, fan, step=31):
+  """What decoupling slot from lane would buy: greedy 8-colouring (+ swap refinement) of the local vertices of
+  every `step`-th tile so that the distinct vertices a quarter-warp reads at one fan step fall into different
+  bank groups.  Returns (excess with slot == local index, excess with the colouring)."""
+  before = after = 0
+  rng = np.random.default_rng(1)
+  for v_begin, nv, nlv, nlt, halo_off, ltri_off, is_fan in tiles[::step]:
+    u = fan_entries(fan[v_begin:v_begin + nv])
+    groups = []
+    for i in range(9):
+      for q in range(16):
+        lo, hi = q * 8, min((q + 1) * 8, nv)
+        if lo < nv:
+          s = np.unique(u[lo:hi, i])
+          if len(s) > 1:
+            groups.append(s)
+    cost = lambda cls: sum(np.bincount(cls[g], minlength=8).max() - 1 for g in groups)
+    before += cost(np.arange(nlv) % 8)
+    member = [[] for _ in range(nlv)]
+    for gi, g in enumerate(groups):
+      for x in g:
+        member[x].append(gi)
+    cap = -(-nlv // 8)
+    cnt = np.zeros(8, int)
+    cls = np.full(nlv, -1)
+    gcount = np.zeros((len(groups), 8), int)
+    for x in np.argsort([-len(mm) for mm in member]):
+      best = None
+      for c in range(8):
+        if cnt[c] >= cap:
+          continue
+        add = sum(1 for gi in member[x] if gcount[gi, c] + 1 > max(1, gcount[gi].max()))
+        if best is None or (add, cnt[c]) < best[0]:
+          best = ((add, cnt[c]), c)
+      c = best[1]
+      cls[x] = c
+      cnt[c] += 1
+      for gi in member[x]:
+        gcount[gi, c] += 1
+    cur = cost(cls)
+    for _ in range(2000):
+      a, b = rng.integers(0, nlv, 2)
+      if cls[a] == cls[b]:
+        continue
+      cls[a], cls[b] = cls[b], cls[a]
+      c = cost(cls)
+      if c <= cur:
+        cur = c
+      else:
+        cls[a], cls[b] = cls[b], cls[a]
+    after += cur
+  return before, after
+
+
 if __name__ == '__main__':
   import test_topology_host as tt
   from voicepuppet_b200 import synthetic
@@ -57,3 +111,6 @@ if __name__ == '__main__':
   n = len(t['tiles'])
   print('tiles %d: ideal gather wavefronts per frame %d, excess %d (%.1f per tile; ncu measured 131.9)' % (n, ideal, total, total / n))
   print('excess per tile by fan entry:', np.round(by_entry / n, 1))
+  if '--colour' in sys.argv:
+    b, a = colouring_potential(t['tiles'], t['fan'])
+    print('8-colouring of the local vertices (every 31st tile): excess %d -> %d' % (b, a))

@@ -159,6 +159,11 @@ void vp_topology_destroy(vp_topology* t);
 int vp_topology_sizes(const vp_topology* t, int* ntiles, int* nltri, int* nhalo);
 int vp_topology_copy(const vp_topology* t, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
                      int* halo, uint16_t* ring, uint32_t* fan);
+/* Optional bank-conflict-aware shared-memory slots of the fan tiles (used by the vertex kernel when the model was
+ * created with VPB200_VERTEX_SLOTS=1): slot_off[ntiles] (offset into slot_tab, -1 for generic tiles),
+ * slot_tab[vp_topology_slot_count()] (slot of local vertex i), fan_slot[nver][5] (fan records in slot space). */
+int vp_topology_slot_count(const vp_topology* t);
+int vp_topology_copy_slots(const vp_topology* t, int* slot_off, uint16_t* slot_tab, uint32_t* fan_slot);
 
 /* Post-raster composite of the frame loop, on the device (voicepuppet/pixrefer/infer_bfmvid.py:111-121 and
  * :234-236): the rasterized frames are resized to size x size exactly like cv2.resize does for 8-bit images

@@ -197,3 +197,20 @@ def test_awkward_mesh_takes_the_generic_path():
     assert np.array_equal(np.isnan(a), np.isnan(b)), name
     assert rel_err(np.nan_to_num(a), np.nan_to_num(b)) <= REL, (name, rel_err(np.nan_to_num(a), np.nan_to_num(b)))
   assert np.isnan(want[2]).any()                          # isolated vertices: 0/0 normals -> NaN colours
+
+
+@pytest.mark.skipif(__import__('os').environ.get('VPB200_TEST_EXPERIMENTAL') != '1',
+                    reason='opt-in kernel flavour, not yet measured on the GPU (set VPB200_TEST_EXPERIMENTAL=1)')
+def test_slot_flavour_of_the_fan_kernel_matches(full_model, monkeypatch):
+  """VPB200_VERTEX_SLOTS=1 at model creation: positions staged at bank-conflict-aware slots.  Same frames."""
+  from voicepuppet_b200 import render
+  from voicepuppet_b200.model import DeviceModel
+  coeffs = synthetic.make_coeffs(20, seed=1)
+  want = np.asarray(render.render_sequence(coeffs, full_model, res=224)).copy()
+  monkeypatch.setenv('VPB200_VERTEX_SLOTS', '1')
+  twin = synthetic.cached_model()                      # a distinct object -> a fresh DeviceModel with slot tables
+  if twin is full_model:
+    import copy
+    twin = copy.copy(full_model)
+  got = np.asarray(render.render_sequence(coeffs, twin, res=224))
+  assert np.array_equal(got, want)                     # same arithmetic, only the shared-memory placement differs

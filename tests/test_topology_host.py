@@ -28,6 +28,10 @@ def build(model):
            halo=np.zeros(nh.value, np.int32), ring=np.zeros((nver, 8), np.uint16),
            fan=np.zeros((nver, 5), np.uint32))
   _lib.check(lib.vp_topology_copy(h, *[_lib.ptr(t[k]) for k in ('v_int2orig', 'tri_int', 'tiles', 'ltri', 'halo', 'ring', 'fan')]))
+  t['slot_off'] = np.zeros(nt.value, np.int32)
+  t['slot_tab'] = np.zeros(max(lib.vp_topology_slot_count(h), 1), np.uint16)
+  t['fan_slot'] = np.zeros((nver, 5), np.uint32)
+  _lib.check(lib.vp_topology_copy_slots(h, _lib.ptr(t['slot_off']), _lib.ptr(t['slot_tab']), _lib.ptr(t['fan_slot'])))
   lib.vp_topology_destroy(h)
   return t, tri, pb
 
@@ -147,3 +151,40 @@ def test_rejects_bad_indices():
   h = ctypes.c_void_p()
   rc = lib.vp_topology_build(ctypes.byref(h), 3, 1, _lib.ptr(tri), _lib.ptr(pb), _lib.ptr(xyz))
   assert rc != 0 and b'out of range' in lib.vp_last_error()
+
+
+def test_slot_tables_keep_the_normals_and_halve_the_bank_conflicts(full_model):
+  """The optional slot tables (VPB200_VERTEX_SLOTS=1): positions staged at slot_tab[local] and gathered through
+  fan_slot give the same normals, and in the quarter-warp bank model (tools/bank_conflict_sim.py, which matches
+  ncu's conflict count for the default tables) the excess wavefronts drop by more than a third."""
+  import os, sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tools'))
+  from bank_conflict_sim import excess_wavefronts
+  t, tri, pb = build(full_model)
+  coeff = synthetic.make_coeffs(1, seed=5)
+  shape = orc.shape_formation(coeff[:, :80], coeff[:, 80:144], full_model)[0].astype(np.float64)
+  want = orc.compute_norm(shape[None], full_model)[0]
+  shape_int = shape[t['v_int2orig']]
+  got = np.zeros_like(want)
+  for ti, (v_begin, nv, nlv, nlt, halo_off, ltri_off, is_fan) in enumerate(t['tiles']):
+    assert is_fan and t['slot_off'][ti] >= 0
+    slots = t['slot_tab'][t['slot_off'][ti]:t['slot_off'][ti] + nlv].astype(np.int64)
+    assert len(set(slots.tolist())) == nlv and slots.max() < nlv + 8            # a valid placement in s_pos
+    local = np.concatenate([np.arange(v_begin, v_begin + nv), t['halo'][halo_off:halo_off + nlv - nv]])
+    staged = np.zeros((nlv + 8, 3))
+    staged[slots] = shape_int[local]                                            # what the kernel's stage() writes
+    # fan_normals reads pos[u] - pos[:nv] with v at local index: own vertex v sits at slot slots[v]
+    fan = t['fan_slot'][v_begin:v_begin + nv].astype(np.int64)
+    off = np.stack([fan[:, 0] & 0xFFFF, fan[:, 0] >> 16, fan[:, 1] & 0xFFFF, fan[:, 1] >> 16, fan[:, 2] & 0xFFFF,
+                    fan[:, 2] >> 16, fan[:, 3] & 0xFFFF, fan[:, 3] >> 16, fan[:, 4] & 0xFFFF], axis=1) // 16
+    mask = fan[:, 4] >> 16
+    v = staged[slots[:nv]]
+    acc = np.zeros((nv, 3))
+    for i in range(8):
+      on = ((mask >> i) & 1).astype(bool)
+      acc[on] += np.cross(staged[off[on, i]] - v[on], staged[off[on, i + 1]] - v[on])
+    got[t['v_int2orig'][v_begin:v_begin + nv]] = acc / np.linalg.norm(acc, axis=1, keepdims=True)
+  assert np.allclose(got, want, rtol=0, atol=1e-12)
+  before, _, _ = excess_wavefronts(t['tiles'][::9], t['fan'])
+  after, _, _ = excess_wavefronts(t['tiles'][::9], t['fan_slot'])
+  assert after < 0.65 * before, (before, after)

@@ -79,6 +79,8 @@ SIGNATURES = {
     'vp_topology_destroy': (None, [_vp]),
     'vp_topology_sizes': (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     'vp_topology_copy': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'vp_topology_slot_count': (_i, [_vp]),
+    'vp_topology_copy_slots': (_i, [_vp, _vp, _vp, _vp]),
     'vp_set_basis_mode': (_i, [_vp, _i]),
     'vp_set_vertex_mode': (_i, [_vp, _i]),
     'vp_model_fan_tiles': (_i, [_vp]),

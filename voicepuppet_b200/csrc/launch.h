@@ -60,11 +60,18 @@ struct Topology {
   std::vector<int> halo;
   std::vector<uint16_t> ring;      // [nver][8] in internal vertex order
   std::vector<uint32_t> fan;       // [nver][kFanWords] in internal vertex order (zeros where the tile is generic)
+  // Optional (build_topology(..., with_slots)): shared-memory slots decoupled from the local numbering.  The
+  // distinct vertices a quarter-warp reads at one fan step should sit in different 16-byte bank groups, so the
+  // local vertices of a fan tile are 8-coloured (bank group = slot % 8) and slot = colour + 8 * rank in colour.
+  std::vector<int> slot_off;       // [ntiles] offset of the tile's slots in slot_tab, -1 for generic tiles
+  std::vector<uint16_t> slot_tab;  // per fan tile nlv entries: shared-memory slot of local vertex i (< nlv + 8)
+  std::vector<uint32_t> fan_slot;  // [nver][kFanWords]: the fan record with slot byte offsets
 };
 
 // tri: [ntri][3] 0-based original vertex ids; point_buf: [nver][8] 0-based original triangle ids
 // (anything outside [0, ntri) is a pad slot); xyz: [nver][3] mean shape used for the spatial order.
-int build_topology(Topology& out, int nver, int ntri, const int* tri, const int* point_buf, const double* xyz);
+int build_topology(Topology& out, int nver, int ntri, const int* tri, const int* point_buf, const double* xyz,
+                   bool with_slots = false);
 
 // Optional per-vertex outputs of the vertex kernel, in the MODEL's (original) vertex order.
 struct ReconOut {
@@ -106,6 +113,11 @@ struct vp_model {
   int* halo = nullptr;
   uint16_t* ring = nullptr;     // [nver][8] local triangle index per point_buf slot
   uint32_t* fan = nullptr;      // [nver][5] fan records (tiles with TileDesc::fan)
+  // optional bank-conflict-aware slot tables (VPB200_VERTEX_SLOTS=1 at model creation; see Topology)
+  int* slot_off = nullptr;
+  uint16_t* slot_tab = nullptr;
+  uint32_t* fan_slot = nullptr;
+  bool have_slots = false;
   int* tile_list = nullptr;     // tile ids: the n_fan_tiles fan tiles first, then the generic ones
   int n_fan_tiles = 0;
   // TMA descriptor of exb for the tcgen05 basis kernel (a CUtensorMap, kept opaque here)

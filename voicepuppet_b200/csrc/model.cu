@@ -1,5 +1,6 @@
 // The device-resident BFM model object (reference utils/bfm_load_data.py:9-21, class BFM) and
 // its per-clip state (identity shape and texture, reconstruct_mesh.py:20-29,58-62).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -60,6 +61,9 @@ void free_model(vp_model* m) {
   cudaFree(m->halo);
   cudaFree(m->ring);
   cudaFree(m->fan);
+  cudaFree(m->slot_off);
+  cudaFree(m->slot_tab);
+  cudaFree(m->fan_slot);
   cudaFree(m->tile_list);
   cudaFree(m->base);
   cudaFree(m->tex);
@@ -103,7 +107,10 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
 
   std::vector<double> xyz((size_t)m->rows);
   for (size_t i = 0; i < xyz.size(); ++i) xyz[i] = load_as_double(meanshape, ms64, i);
-  VP_TRY(build_topology(m->topo, nver, ntri, tri, point_buf, xyz.data()));
+  // VPB200_VERTEX_SLOTS=1: also build the bank-conflict-aware slot tables (opt-in until measured on the GPU)
+  const char* slots_env = std::getenv("VPB200_VERTEX_SLOTS");
+  const bool with_slots = slots_env && std::atoi(slots_env) != 0;
+  VP_TRY(build_topology(m->topo, nver, ntri, tri, point_buf, xyz.data(), with_slots));
   const std::vector<int>& i2o = m->topo.v_int2orig;
 
   if (center) {
@@ -162,6 +169,12 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
   VP_TRY(upload(&m->halo, m->topo.halo));
   VP_TRY(upload(&m->ring, m->topo.ring));
   VP_TRY(upload(&m->fan, m->topo.fan));
+  if (with_slots) {
+    VP_TRY(upload(&m->slot_off, m->topo.slot_off));
+    VP_TRY(upload(&m->slot_tab, m->topo.slot_tab));
+    VP_TRY(upload(&m->fan_slot, m->topo.fan_slot));
+    m->have_slots = true;
+  }
   {
     std::vector<int> order;
     for (int pass = 1; pass >= 0; --pass)

@@ -209,6 +209,9 @@ struct VertexArgs {
   const TileDesc* tiles;
   const int* tile_list;        // blockIdx.x -> tile id (this launch's slice of vp_model::tile_list)
   const uint32_t* fan;
+  const int* slot_off;         // optional slot tables (SLOTS flavour of the fan kernel), see Topology
+  const uint16_t* slot_tab;
+  const uint32_t* fan_slot;
   const uint32_t* ltri;
   const int* halo;
   const uint16_t* ring;
@@ -473,6 +476,14 @@ struct LocalVerts {
     for (int q = 0; q < kSlotsV; ++q)
       if (q < nq_v) pos[tid + q * kTileV] = make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
   }
+  // same, at explicit byte offsets (two 16-bit halves of `offs`): the bank-conflict-aware slot placement
+  __device__ __forceinline__ void stage_at(char* pos, uint32_t offs, int nq_v) const {
+#pragma unroll
+    for (int q = 0; q < kSlotsV; ++q)
+      if (q < nq_v)
+        *reinterpret_cast<float4*>(pos + ((offs >> (16 * q)) & 0xFFFFu)) =
+            make_float4(rx[q] + dx[q], ry[q] + dy[q], rz[q] + dz[q], 0.f);
+  }
   // the staged position of the thread's first local vertex (its own vertex), kept in registers by the fan kernel
   __device__ __forceinline__ float3 own_staged() const { return make_float3(rx[0] + dx[0], ry[0] + dy[0], rz[0] + dz[0]); }
 };
@@ -490,13 +501,17 @@ __device__ __forceinline__ void stage_frame_constants(const VertexArgs& a, Frame
 // run of frames).  Per frame: the own vertex sums (u_i - v) x (u_i+1 - v) over its ring from 9 gathers of
 // staged positions, finishes (finish_vertex), stages the next frame's positions into the other buffer,
 // and the block synchronises once.  Shared memory holds positions only (no per-triangle pass).
-template <int MIN_BLOCKS, bool FAST>
+// SLOTS: local vertex i is staged at shared-memory slot slot_tab[i] instead of i and the fan records come in slot
+// space (fan_slot), which roughly halves the bank conflicts of the gathers in the quarter-warp model
+// (tools/bank_conflict_sim.py); opt-in (VPB200_VERTEX_SLOTS=1 at model creation), not yet measured on the GPU.
+template <int MIN_BLOCKS, bool FAST, bool SLOTS = false>
 __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const VertexArgs a) {
   using Frame = typename std::conditional<FAST, FrameFast, FrameShared>::type;
-  __shared__ float4 s_pos[2][kTileLV];
+  __shared__ float4 s_pos[2][kTileLV + (SLOTS ? 8 : 0)];
   __shared__ __align__(16) Frame s_frame[2];
 
-  const TileDesc td = a.tiles[__ldg(a.tile_list + blockIdx.x)];
+  const int tile_id = __ldg(a.tile_list + blockIdx.x);
+  const TileDesc td = a.tiles[tile_id];
   const int tid = threadIdx.x;
   const int nq_v = (td.nlv + kTileV - 1) / kTileV;  // CTA-uniform
   const int f_begin = blockIdx.y * a.frames_per_block;
@@ -508,9 +523,19 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const Ve
   const bool own = tid < td.nv;
   uint32_t fan[kFanWords] = {0, 0, 0, 0, 0};
   float tr = 0.f, tg = 0.f, tb = 0.f;
-  if (own) {
+  uint32_t slot_offs = 0;  // SLOTS: byte offsets of this thread's two local vertices, 16 bits each
+  if constexpr (SLOTS) {
+    const int so = __ldg(a.slot_off + tile_id);
 #pragma unroll
-    for (int k = 0; k < kFanWords; ++k) fan[k] = __ldg(a.fan + (size_t)lv.gv[0] * kFanWords + k);
+    for (int q = 0; q < kSlotsV; ++q) {
+      const int i = tid + q * kTileV;
+      if (i < td.nlv) slot_offs |= ((uint32_t)__ldg(a.slot_tab + so + i) << 4) << (16 * q);
+    }
+  }
+  if (own) {
+    const uint32_t* fan_tab = SLOTS ? a.fan_slot : a.fan;
+#pragma unroll
+    for (int k = 0; k < kFanWords; ++k) fan[k] = __ldg(fan_tab + (size_t)lv.gv[0] * kFanWords + k);
     if (a.tex) {
       tr = __ldg(a.tex + 3 * (size_t)lv.gv[0]);
       tg = __ldg(a.tex + 3 * (size_t)lv.gv[0] + 1);
@@ -521,8 +546,11 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const Ve
   // prologue: frame f_begin staged, displacement of frame f_begin + 1 in flight
   lv.fetch(a, f_begin, nq_v);
   stage_frame_constants(a, &s_frame[0], f_begin, tid);
-  lv.stage(s_pos[0], tid, nq_v);
-  float3 pv = lv.own_staged();                           // == s_pos[buf][tid], without the shared-memory read
+  if constexpr (SLOTS)
+    lv.stage_at(reinterpret_cast<char*>(s_pos[0]), slot_offs, nq_v);
+  else
+    lv.stage(s_pos[0], tid, nq_v);
+  float3 pv = lv.own_staged();                           // == the own vertex's staged position, without the shared-memory read
   float d0x = lv.dx[0], d0y = lv.dy[0], d0z = lv.dz[0];  // own displacement of the frame being finished
   if (f_begin + 1 < f_end) lv.fetch(a, f_begin + 1, nq_v);
   __syncthreads();
@@ -562,7 +590,10 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const Ve
     // ---- stage frame f + 1 into the other buffers (their readers passed the previous barrier) ----
     if (f + 1 < f_end) {
       stage_frame_constants(a, &s_frame[buf ^ 1], f + 1, tid);
-      lv.stage(s_pos[buf ^ 1], tid, nq_v);
+      if constexpr (SLOTS)
+        lv.stage_at(reinterpret_cast<char*>(s_pos[buf ^ 1]), slot_offs, nq_v);
+      else
+        lv.stage(s_pos[buf ^ 1], tid, nq_v);
       pv = lv.own_staged();
       d0x = lv.dx[0];
       d0y = lv.dy[0];
@@ -684,6 +715,9 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.tiles = m->tiles;
   a.tile_list = m->tile_list;
   a.fan = m->fan;
+  a.slot_off = m->slot_off;
+  a.slot_tab = m->slot_tab;
+  a.fan_slot = m->fan_slot;
   a.ltri = m->ltri;
   a.halo = m->halo;
   a.ring = m->ring;
@@ -727,7 +761,9 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
     dim3 grid(n_fan, (nframes + a.frames_per_block - 1) / a.frames_per_block);
     static const int slow_env = [] { const char* e = std::getenv("VPB200_VERTEX_SLOW"); return e ? std::atoi(e) : 0; }();
     const bool fast = !a.has_out && a.vrec != nullptr && !slow_env;  // raster records only: the folded constants
-    if (fast) {
+    if (fast && m->have_slots) {
+      vertex_fan_kernel<8, true, true><<<grid, kTileV, 0, st>>>(a);
+    } else if (fast) {
       if (minb <= 6)
         vertex_fan_kernel<6, true><<<grid, kTileV, 0, st>>>(a);
       else if (minb == 7)

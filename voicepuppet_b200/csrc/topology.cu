@@ -15,6 +15,7 @@
 //     into at most 9 ring vertices (any manifold mesh: closed or open fans up to valence 8), the tile
 //     also gets FAN records (launch.h), which let the vertex kernel skip the per-triangle pass.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -42,9 +43,115 @@ uint32_t quantize(double v, double lo, double hi) {
   return (uint32_t)q;
 }
 
+
+// ---- bank-conflict-aware shared-memory slots (optional) ---------------------------------------
+// For every fan tile: the "access groups" are the sets of distinct local vertices the 8 lanes of a quarter-warp
+// read at one fan step.  An LDS.128 serialises distinct slots of one bank group (slot % 8), so the local
+// vertices are 8-coloured greedily (most constrained first, balanced colours), refined by swaps that do not
+// increase the number of excess wavefronts, and slot = colour + 8 * rank within the colour.
+void assign_slots(Topology& t) {
+  const int ntiles = (int)t.tiles.size();
+  t.slot_off.assign(ntiles, -1);
+  t.slot_tab.clear();
+  t.fan_slot.assign(t.fan.size(), 0u);
+  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  auto next = [&rng]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); };
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const TileDesc& td = t.tiles[ti];
+    if (!td.fan) continue;
+    const int nlv = td.nlv, nv = td.nv;
+    auto entry = [&](int v, int i) {  // local index of fan entry i of own vertex v
+      const uint32_t* w = &t.fan[(size_t)(td.v_begin + v) * kFanWords];
+      const uint32_t word = w[i >> 1];
+      return (int)((((i & 1) ? (word >> 16) : word) & 0xFFFFu) >> 4);
+    };
+    // access groups
+    std::vector<std::vector<int>> groups;
+    for (int i = 0; i < kFanEntries; ++i)
+      for (int q = 0; q * 8 < nv; ++q) {
+        std::vector<int> g;
+        for (int v = q * 8; v < std::min(nv, q * 8 + 8); ++v) {
+          const int x = entry(v, i);
+          if (std::find(g.begin(), g.end(), x) == g.end()) g.push_back(x);
+        }
+        if (g.size() > 1) groups.push_back(g);
+      }
+    std::vector<std::vector<int>> member(nlv);
+    for (int gi = 0; gi < (int)groups.size(); ++gi)
+      for (int x : groups[gi]) member[x].push_back(gi);
+    const int cap = (nlv + 7) / 8;
+    std::vector<int> cls(nlv, -1), cnt(8, 0), order(nlv);
+    std::vector<std::array<int, 8>> gc(groups.size());
+    for (auto& a : gc) a.fill(0);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return member[a].size() > member[b].size(); });
+    auto gmax = [&](int gi) { return *std::max_element(gc[gi].begin(), gc[gi].end()); };
+    for (int x : order) {
+      int best_c = -1, best_add = 1 << 30, best_cnt = 1 << 30;
+      for (int c = 0; c < 8; ++c) {
+        if (cnt[c] >= cap) continue;
+        int add = 0;
+        for (int gi : member[x]) add += (gc[gi][c] + 1 > std::max(1, gmax(gi)));
+        if (add < best_add || (add == best_add && cnt[c] < best_cnt)) {
+          best_c = c;
+          best_add = add;
+          best_cnt = cnt[c];
+        }
+      }
+      cls[x] = best_c;
+      ++cnt[best_c];
+      for (int gi : member[x]) ++gc[gi][best_c];
+    }
+    // refinement: swap the colours of two vertices when the affected groups do not get worse
+    auto excess_of = [&](const std::vector<int>& gis) {
+      int e = 0;
+      for (int gi : gis) e += gmax(gi) - 1;
+      return e;
+    };
+    for (int it = 0; it < 1500 && nlv > 1; ++it) {
+      const int a = (int)(next() % (uint32_t)nlv), b = (int)(next() % (uint32_t)nlv);
+      if (cls[a] == cls[b]) continue;
+      std::vector<int> aff = member[a];
+      for (int gi : member[b])
+        if (std::find(aff.begin(), aff.end(), gi) == aff.end()) aff.push_back(gi);
+      const int before = excess_of(aff);
+      auto move = [&](int x, int from, int to) {
+        for (int gi : member[x]) {
+          --gc[gi][from];
+          ++gc[gi][to];
+        }
+      };
+      const int ca = cls[a], cb = cls[b];
+      move(a, ca, cb);
+      move(b, cb, ca);
+      if (excess_of(aff) <= before) {
+        cls[a] = cb;
+        cls[b] = ca;
+      } else {
+        move(a, cb, ca);
+        move(b, ca, cb);
+      }
+    }
+    // slots and the fan records in slot space
+    t.slot_off[ti] = (int)t.slot_tab.size();
+    std::vector<int> rank(8, 0), slot(nlv);
+    for (int x = 0; x < nlv; ++x) {
+      slot[x] = cls[x] + 8 * rank[cls[x]]++;
+      t.slot_tab.push_back((uint16_t)slot[x]);
+    }
+    for (int v = 0; v < nv; ++v) {
+      const uint32_t* w = &t.fan[(size_t)(td.v_begin + v) * kFanWords];
+      uint32_t* o = &t.fan_slot[(size_t)(td.v_begin + v) * kFanWords];
+      for (int k = 0; k < 4; ++k) o[k] = ((uint32_t)slot[entry(v, 2 * k)] << 4) | ((uint32_t)slot[entry(v, 2 * k + 1)] << 20);
+      o[4] = ((uint32_t)slot[entry(v, 8)] << 4) | (w[4] & 0xFFFF0000u);
+    }
+  }
+}
+
 }  // namespace
 
-int build_topology(Topology& out, int nver, int ntri, const int* tri, const int* point_buf, const double* xyz) {
+int build_topology(Topology& out, int nver, int ntri, const int* tri, const int* point_buf, const double* xyz,
+                   bool with_slots) {
   VP_REQUIRE(nver >= 0 && ntri >= 0, "negative element count");
   VP_REQUIRE(nver == 0 || (point_buf && xyz), "null model array");
   VP_REQUIRE(ntri == 0 || tri, "null triangle array");
@@ -227,6 +334,7 @@ int build_topology(Topology& out, int nver, int ntri, const int* tri, const int*
     }
     out.tiles.push_back(td);
   }
+  if (with_slots) assign_slots(out);
   return VP_OK;
 }
 
@@ -242,7 +350,7 @@ extern "C" int vp_topology_build(vp_topology** out, int nver, int ntri, const in
   VP_REQUIRE(out != nullptr, "null out pointer");
   *out = nullptr;
   vp_topology* h = new vp_topology();
-  const int rc = vp::build_topology(h->t, nver, ntri, tri, point_buf, xyz);
+  const int rc = vp::build_topology(h->t, nver, ntri, tri, point_buf, xyz, true);
   if (rc != VP_OK) {
     delete h;
     return rc;
@@ -272,5 +380,18 @@ extern "C" int vp_topology_copy(const vp_topology* h, int* v_int2orig, int* tri_
   if (halo) std::memcpy(halo, t.halo.data(), t.halo.size() * sizeof(int));
   if (ring) std::memcpy(ring, t.ring.data(), t.ring.size() * sizeof(uint16_t));
   if (fan) std::memcpy(fan, t.fan.data(), t.fan.size() * sizeof(uint32_t));
+  return VP_OK;
+}
+
+/* The optional slot tables (always built by vp_topology_build): slot_off[ntiles] (-1 = generic tile),
+ * slot_tab[vp_topology_slot_count()], fan_slot[nver][5]. */
+extern "C" int vp_topology_slot_count(const vp_topology* h) { return h ? (int)h->t.slot_tab.size() : -1; }
+
+extern "C" int vp_topology_copy_slots(const vp_topology* h, int* slot_off, uint16_t* slot_tab, uint32_t* fan_slot) {
+  VP_REQUIRE(h != nullptr, "null handle");
+  const vp::Topology& t = h->t;
+  if (slot_off) std::memcpy(slot_off, t.slot_off.data(), t.slot_off.size() * sizeof(int));
+  if (slot_tab) std::memcpy(slot_tab, t.slot_tab.data(), t.slot_tab.size() * sizeof(uint16_t));
+  if (fan_slot) std::memcpy(fan_slot, t.fan_slot.data(), t.fan_slot.size() * sizeof(uint32_t));
   return VP_OK;
 }

@@ -58,7 +58,10 @@ constexpr int kPrefetchTiles = 4;         // L2 prefetch distance of the TMA pro
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;
 
 inline int tc_smem_bytes(int n_mma, bool bulk) { return off_b(bulk) + 2 * n_mma * 256 + (bulk ? n_mma * 512 : 0) + 128; }
-constexpr int kMaxDynSmem = 232448;  // 227 KB
+// dynamic shared memory both flavours may ask for: what the default flavour needs for 128 frames (229,504 B, known
+// to be accepted; the opt-in limit of the part is 232,448 B)
+inline int max_dyn_smem() { return tc_smem_bytes(128, false); }
+bool g_bulk_ok = false;
 
 // 3xTF32 split by truncation: hi keeps the 19 bits the tensor core reads, lo = x - hi is exact in fp32
 // (|lo| < 2^-10 |x|) and is truncated to its own top 19 bits by the tensor core: 2^-21 relative overall.
@@ -386,7 +389,10 @@ int basis_tc_prepare(vp_model* m) {
   }
   std::memcpy(m->tmap_exb, &map, sizeof(map));
   VP_CUDA(cudaFuncSetAttribute(basis_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcN, false)));
-  VP_CUDA(cudaFuncSetAttribute(basis_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  // the opt-in flavour must never take the default one down with it
+  g_bulk_ok = cudaFuncSetAttribute(basis_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem()) ==
+              cudaSuccess;
+  (void)cudaGetLastError();
   m->have_tmap = true;
   return VP_OK;
 }
@@ -408,7 +414,7 @@ int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nfram
     const int n = std::min(kTcN, nframes - t0);
     const int n_mma = (n + 15) & ~15;
     static const int bulk_env = [] { const char* e = std::getenv("VPB200_BASIS_EPI"); return e ? std::atoi(e) : 0; }();
-    if (bulk_env && trace_dev == nullptr && tc_smem_bytes(n_mma, true) <= kMaxDynSmem)
+    if (bulk_env && g_bulk_ok && trace_dev == nullptr && tc_smem_bytes(n_mma, true) <= max_dyn_smem())
       basis_tc_kernel<true><<<grid, kTcThreads, tc_smem_bytes(n_mma, true), st>>>(
           map, ex_dev + (size_t)t0 * VP_N_EX, disp_dev + (size_t)t0 * m->rows_pad, n, m->rows_pad, ntiles, trace_dev,
           store_policy);

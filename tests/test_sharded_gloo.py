@@ -71,3 +71,22 @@ def test_two_rank_gather_equals_single_process(n_frames):
   want = pipeline.render_sequence(synthetic.make_coeffs(n_frames, seed=9), model, res, 'jitter')
   assert got.shape == want.shape and np.array_equal(got, want)
   assert want.any()
+
+
+def test_push_plan_covers_every_frame(monkeypatch):
+  """Chunk plans of the push gather (render.push_plan): positive chunks adding up to the shard, short first and
+  last chunks for long shards, one chunk for short ones; VPB200_PUSH_PLAN overrides only when it adds up."""
+  from voicepuppet_b200 import render
+  monkeypatch.delenv('VPB200_PUSH_PLAN', raising=False)
+  for world in (2, 4, 8):
+    for n in (1, 7, 47, 48, 75, 150, 1500):
+      plan = render.push_plan(n, world)
+      assert sum(plan) == n and min(plan) > 0
+      if n < 48:
+        assert plan == [n]
+      else:
+        assert len(plan) >= 4 and plan[0] <= n // 4 and plan[-1] <= n // 4
+  assert render.push_plan(75, 8) == [9, 29, 28, 9]
+  monkeypatch.setenv('VPB200_PUSH_PLAN', '25,25,25')
+  assert render.push_plan(75, 8) == [25, 25, 25]
+  assert render.push_plan(76, 8) != [25, 25, 25]          # does not add up: ignored

@@ -469,18 +469,38 @@ def render_face_sequence(center_x, center_y, ratio, coeffs, img_shape, transform
                             inputs, channel_offset, want_canvas)
 
 
-def render_face(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel):
-  """Same signature and result as infer_bfmvid.py:79-122 (one frame, jitter globals advanced): reconstruction,
-  rasterization, channel swap, cv2.resize-exact resize and paste all run on the GPU; the returned canvas is a
-  numpy uint8 array of ``img``'s shape, like the reference's."""
+def _render_face_one(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel, angles):
+  """One frame through the GPU path: reconstruction + rasterization at 224x224, channel swap, cv2.resize-exact
+  resize and paste; returns the canvas as a numpy array of ``img``'s shape and dtype."""
   import torch
-  ang = _state.step().copy()
   dev = torch.device('cuda', 0)
   frames = torch.empty((1, IMG, IMG, 3), dtype=torch.uint8, device=dev)
   with torch.cuda.device(dev):
-    render_sequence(np.asarray(bfmcoeff).reshape(1, 257), facemodel, res=IMG, angles=ang, device=0, out=frames)
+    render_sequence(np.asarray(bfmcoeff).reshape(1, 257), facemodel, res=IMG, angles=angles, device=0, out=frames)
     try:
       canvas, _ = composite_device(frames, center_x, center_y, ratio, transform_params, (img.shape[0], img.shape[1]))
     except Exception as e:   # numpy raises ValueError when the face does not fit the canvas (:121)
       raise ValueError(str(e))
   return canvas[0].cpu().numpy().astype(img.dtype, copy=False)
+
+
+def render_face(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel):
+  """Same signature and result as voicepuppet/pixrefer/infer_bfmvid.py:79-122 (one frame, jitter globals
+  advanced, Reconstruction_rotation with the jitter angles): reconstruction, rasterization, channel swap,
+  cv2.resize-exact resize and paste all run on the GPU; the returned canvas is a numpy uint8 array of ``img``'s
+  shape, like the reference's."""
+  ang = _state.step().copy()
+  return _render_face_one(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel, ang)
+
+
+def render_face_pixflow(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel):
+  """The copy of render_face in voicepuppet/pixflow/infer_bfm_pixflow.py:72-115: the jitter update is commented
+  out there (:78-82), so Reconstruction_rotation always gets the module's initial angles [[0, 0, 0]]."""
+  return _render_face_one(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel,
+                          np.zeros((1, 3), dtype=np.float32))
+
+
+def render_face_dataset(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel):
+  """The copy of render_face in datasets/make_data_from_GRID.py:516-552 (dataset preparation): Reconstruction
+  with the coefficient row's own angles, single rotation."""
+  return _render_face_one(center_x, center_y, ratio, bfmcoeff, img, transform_params, facemodel, None)

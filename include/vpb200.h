@@ -173,6 +173,8 @@ int vp_topology_copy_slots(const vp_topology* t, int* slot_off, uint16_t* slot_t
  * order (what lands in PixReferNet's inputs[..., 3:6]).  All pointers are device pointers; asynchronous on
  * `stream`.  A face that does not fit the canvas is VP_ERR_ARG (numpy raises at :121).
  * vp_composite_placement evaluates :80-82 and :112-121: size = round(res / (ratio * tp[2])), x0 / y0. */
+/* Host only (no device needed): the per-axis coefficient table [dsize][4] = (s0, s1, c0, c1) vp_composite_dev uses. */
+int vp_composite_axis_table(int ssize, int dsize, int is_y, int* out4);
 int vp_composite_placement(int res, int center_x, int center_y, double ratio, const double* transform_params5,
                            int* size, int* x0, int* y0);
 int vp_composite_dev(const unsigned char* frames_dev, int nframes, int res, int size, int x0, int y0,

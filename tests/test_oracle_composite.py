@@ -60,3 +60,17 @@ def test_c_abi_placement_matches_the_reference_lines():
   for cx, cy, ratio, tp in cases:
     for res in (224, 256):
       assert render.composite_placement(cx, cy, ratio, tp, res) == oc.placement(cx, cy, ratio, np.array(tp), res), (cx, cy, ratio, tp, res)
+
+
+def test_c_abi_axis_tables_match_the_cv2_pinned_oracle():
+  """The C++ builder of the resize coefficient tables (host code of csrc/composite.cu) over many size pairs."""
+  from voicepuppet_b200 import _lib
+  lib = _lib.lib()
+  rng = np.random.Generator(np.random.PCG64(17))
+  pairs = [(224, s) for s in range(60, 460, 7)] + [(int(a), int(b)) for a, b in rng.integers(8, 700, (120, 2))]
+  for ssize, dsize in pairs:
+    for is_y in (0, 1):
+      out = np.zeros((dsize, 4), np.int32)
+      _lib.check(lib.vp_composite_axis_table(ssize, dsize, is_y, _lib.ptr(out)))
+      s0, s1, c0, c1 = oc.axis_table(ssize, dsize, bool(is_y))
+      assert np.array_equal(out, np.stack([s0, s1, c0, c1], axis=1)), (ssize, dsize, is_y)

@@ -67,6 +67,7 @@ SIGNATURES = {
     'vp_rasterize_triangles_core': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     'vp_render_texture_core': (_i, [_vp] * 7 + [_i] * 10),
     'vp_get_normal_core': (_i, [_vp, _vp, _vp, _i, _i]),
+    'vp_composite_axis_table': (_i, [_i, _i, _i, _vp]),
     'vp_composite_placement': (_i, [_i, _i, _i, ctypes.c_double, _vp, _vp, _vp, _vp]),
     'vp_composite_dev': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     'vp_render_colors_batch_dev': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

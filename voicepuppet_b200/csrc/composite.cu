@@ -129,6 +129,20 @@ __global__ void __launch_bounds__(256) composite_kernel(const CompositeArgs a) {
 
 using namespace vp;
 
+// Host only: the resize coefficient table of one axis, [dsize][4] = (s0, s1, c0, c1) per destination index, as the
+// kernel uses it (lets the CPU test-suite compare the table builder with the cv2-pinned oracle over many sizes).
+extern "C" int vp_composite_axis_table(int ssize, int dsize, int is_y, int* out4) {
+  VP_REQUIRE(ssize > 0 && dsize > 0 && out4 != nullptr, "bad argument");
+  const std::vector<AxisEntry> t = axis_table(ssize, dsize, is_y != 0);
+  for (int d = 0; d < dsize; ++d) {
+    out4[4 * d] = t[(size_t)d].s0;
+    out4[4 * d + 1] = t[(size_t)d].s1;
+    out4[4 * d + 2] = t[(size_t)d].c0;
+    out4[4 * d + 3] = t[(size_t)d].c1;
+  }
+  return VP_OK;
+}
+
 // infer_bfmvid.py:80-82,112-121: size and top-left corner of the pasted face.
 extern "C" int vp_composite_placement(int res, int center_x, int center_y, double ratio, const double* transform_params5,
                                       int* size, int* x0, int* y0) {

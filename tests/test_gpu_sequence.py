@@ -134,3 +134,20 @@ def test_contact_sheet_matches_cpu_reference(small_model, tmp_path):
   assert not sheet[6 * 224:].any() and not sheet[2 * 224:3 * 224].any()
   bfm_visual.plot_bfm_coeff_seq(str(tmp_path), small_model, 1000, [t], real, pred)
   assert (tmp_path / 'bfmnet_1000.jpg').stat().st_size > 1000
+
+
+@pytest.mark.skipif(__import__('os').environ.get('VPB200_TEST_EXPERIMENTAL') != '1' or
+                    __import__('os').environ.get('VPB200_HOST_PIPE') != '1',
+                    reason='opt-in host pipeline, not yet measured on the GPU (VPB200_TEST_EXPERIMENTAL=1 VPB200_HOST_PIPE=1)')
+def test_stage_parallel_host_pipeline_renders_the_same_frames(full_model):
+  """VPB200_HOST_PIPE=1 (read once per process): K2 of the next chunk under K3/K4 of the current one.  The frames
+  must equal the device-output rendering of the same sequence (default pipeline), masks included."""
+  import torch
+  for t in (16, 75, 130):
+    coeffs = synthetic.make_coeffs(t, seed=5)
+    host, mask = render.render_sequence(coeffs, full_model, res=256, want_mask=True)            # host outputs: the pipeline
+    dev = torch.empty((t, 256, 256, 3), dtype=torch.uint8, device='cuda:0')
+    render.render_sequence(coeffs, full_model, res=256, out=dev)                                # device outputs: ChunkRunner
+    torch.cuda.synchronize()
+    assert np.array_equal(np.asarray(host), dev.cpu().numpy()), t
+    assert mask.any()

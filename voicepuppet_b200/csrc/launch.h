@@ -140,6 +140,10 @@ struct vp_model {
   // the two halves of the chunk workspaces), so the ramp-up of one chunk's kernels fills the tails of the other's
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_basis = nullptr, ev_aux_done = nullptr, ev_main_done = nullptr;
+  // opt-in stage-parallel host pipeline (VPB200_HOST_PIPE=1, sequence.cu): a high-priority stream for K1/K3/K4 in
+  // chunk order, the vertex kernel of the next chunk underneath on aux_stream; created on first use
+  cudaStream_t hi_stream = nullptr;
+  cudaEvent_t ev_k2[2] = {nullptr, nullptr}, ev_k3[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 

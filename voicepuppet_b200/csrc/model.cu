@@ -87,6 +87,9 @@ void free_model(vp_model* m) {
   for (cudaEvent_t e : {m->ev_fork, m->ev_basis, m->ev_aux_done, m->ev_main_done})
     if (e) cudaEventDestroy(e);
   if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
+  if (m->hi_stream) cudaStreamDestroy(m->hi_stream);
+  for (cudaEvent_t e : {m->ev_k2[0], m->ev_k2[1], m->ev_k3[0], m->ev_k3[1]})
+    if (e) cudaEventDestroy(e);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   (void)cudaGetLastError();
   delete m;

@@ -200,6 +200,95 @@ struct ChunkRunner {
   }
 };
 
+// Opt-in (VPB200_HOST_PIPE=1) host-output pipeline, stage-parallel instead of chunk-parallel: the chunks keep their
+// order on a high-priority stream (K1, then K3 and K4 of every chunk, each followed by its device->host copy on
+// the copy stream) while the vertex kernel of the NEXT chunk runs underneath on the low-priority auxiliary stream.
+// K2 is bound by the LSU data pipe and K3 by instruction issue, so they share an SM well, and unlike two whole
+// chunks in flight this does not delay the first chunk, which is what the PCIe drain waits for.  Written from the
+// round-1 measurements (per-chunk 68 us against 67 us of drain per 19 frames); not yet measured on the GPU.
+int render_host_pipelined(vp_model* m, int T, int res, int chunk, int first, const float* ex_dev,
+                          const FrameParams* params_dev, int rotate_first, unsigned char* image, unsigned char* face_mask,
+                          cudaStream_t st) {
+  if (!m->hi_stream) {
+    int least = 0, greatest = 0;
+    VP_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    VP_CUDA(cudaStreamCreateWithPriority(&m->hi_stream, cudaStreamNonBlocking, greatest));
+    for (int i = 0; i < 2; ++i) {
+      VP_CUDA(cudaEventCreateWithFlags(&m->ev_k2[i], cudaEventDisableTiming));
+      VP_CUDA(cudaEventCreateWithFlags(&m->ev_k3[i], cudaEventDisableTiming));
+    }
+  }
+  cudaStream_t H = m->hi_stream, L = m->aux_stream;
+  const size_t npix = (size_t)res * res;
+  const int group = basis_group_frames(chunk, T);
+  const int nchunks_est = 4 + (T + chunk - 1) / chunk + T / 96;
+  // workspaces: two vertex-record slots (K2 of chunk c+1 writes one while K3 of chunk c reads the other)
+  VP_CUDA(m->ws_disp.reserve((size_t)group * m->rows_pad * sizeof(float), m->device));
+  VP_CUDA(m->ws_vrec.reserve((size_t)2 * chunk * m->vrec_stride * sizeof(float4), m->device));
+  VP_CUDA(m->ws_tricol.reserve((size_t)2 * chunk * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
+  void* before = m->ws_keys.ptr;
+  VP_CUDA(m->ws_keys.reserve((size_t)2 * chunk * npix * sizeof(unsigned long long), m->device));
+  if (m->ws_keys.ptr != before) m->key_epoch = 0;
+  if (m->key_epoch == 0 || m->key_epoch + (uint32_t)nchunks_est + 2u >= epoch_limit(m->ntri)) {
+    VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
+    m->key_epoch = 0;
+  }
+  for (int b = 0; b < 2; ++b) {
+    VP_CUDA(m->ws_img[b].reserve((size_t)chunk * npix * 3, m->device));
+    if (face_mask) VP_CUDA(m->ws_mask[b].reserve((size_t)chunk * npix, m->device));
+  }
+  const void* fc = nullptr;
+  VP_TRY(prepare_frame_constants(m, params_dev, T, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, st, &fc));
+  const char* fconst = static_cast<const char*>(fc);
+  VP_CUDA(cudaEventRecord(m->ev_fork, st));       // uploads, frame constants, z-buffer clear: before anything below
+  VP_CUDA(cudaStreamWaitEvent(H, m->ev_fork, 0));
+  VP_CUDA(cudaStreamWaitEvent(L, m->ev_fork, 0));
+  ReconOut none;
+  int ci = 0;
+  for (int t0 = 0, n = 0; t0 < T; t0 += n, ++ci) {
+    n = std::min(std::min(t0 == 0 ? first : chunk, T - t0), group - t0 % group);
+    const int slot = ci & 1;
+    if (ex_dev && t0 % group == 0) {              // K1 of the group on H (after K3/K4 of the previous group's chunks)
+      if (ci > 0) VP_CUDA(cudaStreamWaitEvent(H, m->ev_k2[(ci - 1) & 1], 0));  // its last K2 has read ws_disp
+      VP_TRY(launch_basis(m, ex_dev + (size_t)t0 * VP_N_EX, m->ws_disp.as<float>(), std::min(group, T - t0), H));
+      VP_CUDA(cudaEventRecord(m->ev_basis, H));
+      VP_CUDA(cudaStreamWaitEvent(L, m->ev_basis, 0));
+    }
+    float4* vrec = m->ws_vrec.as<float4>() + (size_t)slot * chunk * m->vrec_stride;
+    unsigned long long* keys = m->ws_keys.as<unsigned long long>() + (size_t)slot * chunk * npix;
+    uint32_t* tricol = m->ws_tricol.as<uint32_t>() + (size_t)slot * chunk * std::max(m->ntri, 1);
+    const float* disp = ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr;
+    // ---- K2 of this chunk on L, once K3 of chunk ci - 2 no longer reads this slot's vertex records ----------------
+    if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(L, m->ev_k3[slot], 0));
+    VP_TRY(launch_vertex(m, disp, params_dev + t0, n, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, vrec, none,
+                         L, fconst + (size_t)t0 * frame_constants_stride()));
+    VP_CUDA(cudaEventRecord(m->ev_k2[slot], L));
+    // ---- K3, K4 on H in chunk order, then the drain -----------------------------------------------------------------
+    VP_CUDA(cudaStreamWaitEvent(H, m->ev_k2[slot], 0));
+    if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(H, m->ev_copy[slot], 0));   // staging image of chunk ci - 2 has drained
+    const uint32_t epoch = ++m->key_epoch;
+    VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, epoch, n, m->ntri, res, res, H));
+    VP_CUDA(cudaEventRecord(m->ev_k3[slot], H));
+    unsigned char* img = m->ws_img[slot].as<unsigned char>();
+    unsigned char* msk = face_mask ? m->ws_mask[slot].as<unsigned char>() : nullptr;
+    VP_TRY(launch_resolve_packed(keys, tricol, m->t_orig2int_dev, epoch, img, msk, n, m->ntri, res, res, H));
+    VP_CUDA(cudaEventRecord(m->ev_render[slot], H));
+    VP_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_render[slot], 0));
+    VP_CUDA(cudaMemcpyAsync(image + (size_t)t0 * npix * 3, img, (size_t)n * npix * 3, cudaMemcpyDeviceToHost, m->copy_stream));
+    if (face_mask)
+      VP_CUDA(cudaMemcpyAsync(face_mask + (size_t)t0 * npix, msk, (size_t)n * npix, cudaMemcpyDeviceToHost, m->copy_stream));
+    VP_CUDA(cudaEventRecord(m->ev_copy[slot], m->copy_stream));
+  }
+  // join everything back onto the caller's stream, then wait (the call returns frames in host memory)
+  VP_CUDA(cudaEventRecord(m->ev_main_done, H));
+  VP_CUDA(cudaStreamWaitEvent(st, m->ev_main_done, 0));
+  VP_CUDA(cudaEventRecord(m->ev_aux_done, L));
+  VP_CUDA(cudaStreamWaitEvent(st, m->ev_aux_done, 0));
+  VP_CUDA(cudaStreamSynchronize(st));
+  VP_CUDA(cudaStreamSynchronize(m->copy_stream));
+  return VP_OK;
+}
+
 int check_sequence_args(const vp_model* m, int nframes, int res, const void* image) {
   VP_REQUIRE(m != nullptr, "null model");
   VP_REQUIRE(nframes >= 0, "nframes >= 0");
@@ -357,6 +446,19 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
   // matters is how soon it starts: the first chunk is short, the following ones full-sized.
   const int first = (outputs_on_device || forced_chunk || T < 4 * 8) ? chunk : std::max(6, chunk / 3);
   const int nchunks_est = 2 + (T + chunk - 1) / chunk + T / 96;
+  static const int host_pipe = [] { const char* e = std::getenv("VPB200_HOST_PIPE"); return e ? std::atoi(e) : 0; }();
+  if (host_pipe && !outputs_on_device && !m->profiling && T >= 16) {
+    const int rc_pipe = render_host_pipelined(m, T, res, chunk, first, ex_dev, params_dev, fr->rotate_shape_first, image,
+                                              face_mask, st);
+    if (rc_pipe != VP_OK) {
+      m->key_epoch = 0;
+      cudaStreamSynchronize(st);
+      if (m->hi_stream) cudaStreamSynchronize(m->hi_stream);
+      cudaStreamSynchronize(m->aux_stream);
+      cudaStreamSynchronize(m->copy_stream);
+    }
+    return rc_pipe;
+  }
   ChunkRunner run(m, st);
   // host outputs: the PCIe drain is the slow side and wants the FIRST chunk as early as possible, which two
   // chunks in flight delay (measured: 454 vs 417 us per 75-frame call), so that path stays on one stream

@@ -162,6 +162,12 @@ int vp_topology_copy(const vp_topology* t, int* v_int2orig, int* tri_int, int* t
 /* Optional bank-conflict-aware shared-memory slots of the fan tiles (used by the vertex kernel when the model was
  * created with VPB200_VERTEX_SLOTS=1): slot_off[ntiles] (offset into slot_tab, -1 for generic tiles),
  * slot_tab[vp_topology_slot_count()] (slot of local vertex i), fan_slot[nver][5] (fan records in slot space). */
+/* Triangle ownership of the fused vertex + raster kernel (csrc/fused.cu): tile i owns rows
+ * own_tri_off[i] .. own_tri_off[i + 1] of tri_int (the triangles whose smallest internal vertex it holds);
+ * own_ltri[j] = the corners of row j as 3 x 10-bit vertex indices local to the owner tile; tri_by_orig[t][4] =
+ * internal vertex ids of ORIGINAL triangle t (+ pad).  Returns 1 when every tile has fan records and every
+ * owned triangle's corners are local to its owner (the fused kernel applies), 0 otherwise, < 0 on error. */
+int vp_topology_copy_owned(const vp_topology* t, int* own_tri_off, uint32_t* own_ltri, int* tri_by_orig);
 int vp_topology_slot_count(const vp_topology* t);
 int vp_topology_copy_slots(const vp_topology* t, int* slot_off, uint16_t* slot_tab, uint32_t* fan_slot);
 
@@ -202,6 +208,14 @@ int vp_set_basis_mode(vp_model* m, int mode);
  * ring-of-faces kernel elsewhere), 1 = always the generic kernel (tests compare the two). */
 int vp_set_vertex_mode(vp_model* m, int mode);
 int vp_model_fan_tiles(const vp_model* m); /* tiles that take the fan path (of vp_model_ntiles) */
+
+/* Chunk pipeline of vp_render_sequence*: 0 = automatic -- the fused vertex + z-buffer kernel (csrc/fused.cu: one
+ * CTA per vertex tile projects its vertices and rasterizes the triangles it owns out of shared memory) whenever
+ * every tile has fan records and every triangle's corners are local to its owner tile (any manifold mesh with a
+ * consistent point_buf: vp_model_fused_available() == 1); 1 = always the separate kernels (vertex records ->
+ * scatter -> resolve), which the tests compare it with bit for bit. */
+int vp_set_raster_path(vp_model* m, int mode);
+int vp_model_fused_available(const vp_model* m);
 
 /* Per-clip constants ("identity mean precomputed once"): base shape = meanshape + idBase.id
  * - center, texture = meantex + texBase.tex.  Either pointer may be NULL to keep the old one. */
@@ -312,9 +326,11 @@ unsigned long long vp_launch_count(void);
 
 /* Per-kernel device time of the last vp_render_sequence(_dev) call when profiling is enabled
  * (CUDA events around each kernel, accumulated over chunks; enabling it makes the _dev variant
- * synchronise).  Four slots: names "basis;vertex;scatter;resolve" (semicolon separated). */
+ * synchronise).  Slots: names "basis;vertex;scatter;resolve;fused" (semicolon separated; "fused" = the fused vertex + scatter kernel, which replaces "vertex" and "scatter" when it applies). */
 int vp_set_profiling(vp_model* m, int enabled);
 int vp_get_profile(vp_model* m, char* names, int names_cap, float* ms, int ms_cap);
+/* launches[k] = number of kernel launches summed into ms[k] of vp_get_profile by the last profiled call. */
+int vp_get_profile_launches(vp_model* m, int* launches, int cap);
 
 #ifdef __cplusplus
 }

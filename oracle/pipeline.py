@@ -105,3 +105,47 @@ def timed_pool_run(coeffs, angles, res, workers, model_kwargs=None, repeats=1):
       dt = time.perf_counter() - t0
       best = dt if best is None else min(best, dt)
   return sum(d[0] for d in done), best
+
+
+# ---- end-to-end triangle-id accounting (BASELINE.json north_star: "bit-exact, apart from a reported count") ----
+def classify_mismatches(v_ref, v_got, triangles, tid_ref, tid_got, near_tie, res, edge_eps=1e-3):
+  """Why do two triangle-id buffers differ?  v_ref / v_got: the float32 raster vertices [3N] of the CPU chain and of
+  the device chain (they differ in the last ulp for some vertices); tid_*: winning triangle per pixel (-1 = none).
+  A mismatching pixel is EXPLAINED when it is a depth near-tie (two nearest depths within 1 ulp, `near_tie`), or an
+  EDGE FLIP: it lies within `edge_eps` (barycentric units, float64) of an edge of one of the two winners and a corner
+  of that winner differs between the two vertex sets -- the inside test of mesh_core.cpp:23-50 flipped because a
+  vertex moved by an ulp.  Returns counts; `unexplained` must be 0."""
+  tid_ref = np.asarray(tid_ref).reshape(-1)
+  tid_got = np.asarray(tid_got).reshape(-1)
+  near_tie = np.asarray(near_tie).reshape(-1).astype(bool)
+  tri = np.asarray(triangles).reshape(-1, 3)
+  vr = np.asarray(v_ref, dtype=np.float32).reshape(-1, 3)
+  vg = np.asarray(v_got, dtype=np.float32).reshape(-1, 3)
+  moved = np.any(vr.view(np.uint32) != vg.view(np.uint32), axis=1)
+  out = {'tri_id_mismatch_px': 0, 'near_tie_px': 0, 'edge_flip_px': 0, 'unexplained_px': 0}
+  for p in np.nonzero(tid_ref != tid_got)[0]:
+    out['tri_id_mismatch_px'] += 1
+    if near_tie[p]:
+      out['near_tie_px'] += 1
+      continue
+    x, y = float(p % res), float(p // res)
+    explained = False
+    for t in (int(tid_ref[p]), int(tid_got[p])):
+      if t < 0:
+        continue
+      a, b, c = tri[t]
+      if not (moved[a] or moved[b] or moved[c]):
+        continue
+      for vv in (vr, vg):
+        p0, p1, p2 = vv[a, :2].astype(np.float64), vv[b, :2].astype(np.float64), vv[c, :2].astype(np.float64)
+        e0, e1, e2 = p2 - p0, p1 - p0, np.array([x, y]) - p0
+        d00, d01, d11, d02, d12 = e0 @ e0, e0 @ e1, e1 @ e1, e0 @ e2, e1 @ e2
+        den = d00 * d11 - d01 * d01
+        if den == 0:
+          explained = True
+          continue
+        u, v = (d11 * d02 - d01 * d12) / den, (d00 * d12 - d01 * d02) / den
+        if min(abs(u), abs(v), abs(1.0 - u - v)) < edge_eps:
+          explained = True
+    out['edge_flip_px' if explained else 'unexplained_px'] += 1
+  return out

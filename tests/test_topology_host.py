@@ -32,6 +32,10 @@ def build(model):
   t['slot_tab'] = np.zeros(max(lib.vp_topology_slot_count(h), 1), np.uint16)
   t['fan_slot'] = np.zeros((nver, 5), np.uint32)
   _lib.check(lib.vp_topology_copy_slots(h, _lib.ptr(t['slot_off']), _lib.ptr(t['slot_tab']), _lib.ptr(t['fan_slot'])))
+  t['own_tri_off'] = np.zeros(nt.value + 1, np.int32)
+  t['own_ltri'] = np.zeros(max(tri.shape[0], 1), np.uint32)
+  t['tri_by_orig'] = np.zeros((max(tri.shape[0], 1), 4), np.int32)
+  t['fused_ok'] = lib.vp_topology_copy_owned(h, _lib.ptr(t['own_tri_off']), _lib.ptr(t['own_ltri']), _lib.ptr(t['tri_by_orig']))
   lib.vp_topology_destroy(h)
   return t, tri, pb
 
@@ -188,3 +192,43 @@ def test_slot_tables_keep_the_normals_and_halve_the_bank_conflicts(full_model):
   before, _, _ = excess_wavefronts(t['tiles'][::9], t['fan'])
   after, _, _ = excess_wavefronts(t['tiles'][::9], t['fan_slot'])
   assert after < 0.65 * before, (before, after)
+
+
+def test_triangle_ownership_tables_of_the_fused_kernel():
+  """csrc/fused.cu: every triangle is owned by exactly one tile (the one holding its smallest internal vertex),
+  its corners decode -- through the owner's local numbering -- to the triangle's own internal vertices, and the
+  resolve pass's table maps an ORIGINAL triangle index to the same corners."""
+  for model in (synthetic.make_model(420, 48), synthetic.cached_model()):
+    t, tri, pb = build(model)
+    assert t['fused_ok'] == 1
+    ntri = tri.shape[0]
+    off = t['own_tri_off']
+    assert off[0] == 0 and off[-1] == ntri and np.all(np.diff(off) >= 0) and np.diff(off).max() <= TILE_LT
+    orig2int = np.empty(model.meanshape.size // 3, np.int64)
+    orig2int[t['v_int2orig']] = np.arange(orig2int.size)
+    for ti, (v_begin, nv, nlv, nlt, halo_off, ltri_off, is_fan) in enumerate(t['tiles']):
+      local = np.concatenate([np.arange(v_begin, v_begin + nv), t['halo'][halo_off:halo_off + nlv - nv]])
+      rows = np.arange(off[ti], off[ti + 1])
+      tri_int = t['tri_int'][rows]
+      smallest = tri_int[:, :3].min(axis=1)
+      assert np.all((smallest >= v_begin) & (smallest < v_begin + nv))
+      lt = t['own_ltri'][rows]
+      corners = np.stack([lt & 1023, (lt >> 10) & 1023, (lt >> 20) & 1023], axis=1)
+      assert corners.max(initial=0) < nlv
+      assert np.array_equal(local[corners], tri_int[:, :3])
+    assert np.array_equal(np.sort(t['tri_int'][:, 3]), np.arange(ntri))          # every original triangle once
+    assert np.array_equal(t['tri_by_orig'][:, :3], orig2int[tri])
+
+
+def test_inconsistent_point_buf_disables_the_fused_kernel():
+  """A point_buf row that omits one of the vertex's faces: the owner tile may not have staged all the corners
+  of a triangle it owns, so the fused kernel must be refused (the separate kernels take the mesh)."""
+  model = synthetic.make_model(420, 48)
+  t, tri, pb = build(model)
+  assert t['fused_ok'] == 1
+  import copy
+  broken = copy.copy(model)
+  broken.point_buf = np.array(model.point_buf, copy=True)
+  broken.point_buf[:, :] = tri.shape[0] + 1        # every row padded out: no vertex lists any face
+  t2, _, _ = build(broken)
+  assert t2['fused_ok'] == 0

@@ -80,10 +80,13 @@ SIGNATURES = {
     'vp_topology_destroy': (None, [_vp]),
     'vp_topology_sizes': (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     'vp_topology_copy': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'vp_topology_copy_owned': (_i, [_vp, _vp, _vp, _vp]),
     'vp_topology_slot_count': (_i, [_vp]),
     'vp_topology_copy_slots': (_i, [_vp, _vp, _vp, _vp]),
     'vp_set_basis_mode': (_i, [_vp, _i]),
     'vp_set_vertex_mode': (_i, [_vp, _i]),
+    'vp_set_raster_path': (_i, [_vp, _i]),
+    'vp_model_fused_available': (_i, [_vp]),
     'vp_model_fan_tiles': (_i, [_vp]),
     'vp_set_identity': (_i, [_vp, _vp, _vp]),
     'vp_set_base_shape': (_i, [_vp, _vp]),
@@ -106,6 +109,7 @@ SIGNATURES = {
     'vp_launch_count': (ctypes.c_ulonglong, []),
     'vp_set_profiling': (_i, [_vp, _i]),
     'vp_get_profile': (_i, [_vp, ctypes.c_char_p, _i, _vp, _i]),
+    'vp_get_profile_launches': (_i, [_vp, _vp, _i]),
 }
 
 _lib = None

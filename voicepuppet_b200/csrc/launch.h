@@ -19,6 +19,7 @@ int launch_scatter_generic(int mode, const float* vertices, size_t frame_stride,
 // Fused path: keys carry the chunk's epoch in their top bits (see EpochKey in raster.cuh), so the
 // z-buffer is cleared only when the epoch counter wraps (epoch_limit) or the buffer is reallocated.
 uint32_t epoch_limit(int ntri);
+int inline_box_pixels();
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
                           unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
                           int w, cudaStream_t st);
@@ -66,6 +67,12 @@ struct Topology {
   std::vector<int> slot_off;       // [ntiles] offset of the tile's slots in slot_tab, -1 for generic tiles
   std::vector<uint16_t> slot_tab;  // per fan tile nlv entries: shared-memory slot of local vertex i (< nlv + 8)
   std::vector<uint32_t> fan_slot;  // [nver][kFanWords]: the fan record with slot byte offsets
+  // Triangle ownership for the fused vertex + raster kernel (fused.cu): a triangle belongs to the tile of its
+  // smallest internal vertex; tri_int is sorted by that vertex, so a tile owns a contiguous run of it.
+  std::vector<int> own_tri_off;    // [ntiles + 1] run of tri_int rows owned by tile i
+  std::vector<uint32_t> own_ltri;  // [ntri] 3 x 10-bit local vertex indices of tri_int row j in its OWNER's numbering
+  std::vector<int> tri_by_orig;    // [ntri][4] internal vertex ids of ORIGINAL triangle t (+ pad): the resolve pass's gather
+  bool fused_ok = false;           // every tile has fan records and every owned triangle's corners are local to its owner
 };
 
 // tri: [ntri][3] 0-based original vertex ids; point_buf: [nver][8] 0-based original triangle ids
@@ -118,6 +125,12 @@ struct vp_model {
   uint16_t* slot_tab = nullptr;
   uint32_t* fan_slot = nullptr;
   bool have_slots = false;
+  // fused vertex + raster kernel (fused.cu): triangle ownership tables, see Topology
+  int* own_tri_off = nullptr;
+  uint32_t* own_ltri = nullptr;
+  int4* tri_by_orig = nullptr;  // [ntri] internal vertex ids of ORIGINAL triangle t
+  bool fused_ok = false;
+  int fused_mode = 0;           // 0 = fused kernel when the mesh allows it, 1 = separate vertex / scatter / resolve kernels
   int* tile_list = nullptr;     // tile ids: the n_fan_tiles fan tiles first, then the generic ones
   int n_fan_tiles = 0;
   // TMA descriptor of exb for the tcgen05 basis kernel (a CUtensorMap, kept opaque here)
@@ -130,7 +143,7 @@ struct vp_model {
   bool have_base = false, have_tex = false;
 
   // workspaces (grow only)
-  vp::DevBuf ws_fshared, ws_ex, ws_params, ws_disp, ws_vrec, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
+  vp::DevBuf ws_fshared, ws_ex, ws_params, ws_disp, ws_vrec, ws_vcol, ws_keys, ws_tricol, ws_img[2], ws_mask[2], ws_out;
   uint32_t key_epoch = 0;       // epoch of the last chunk rendered into ws_keys (0 = buffer must be cleared)
   // page-locked staging of the per-frame inputs (so their upload is a real async copy)
   void* h_stage = nullptr;
@@ -140,10 +153,6 @@ struct vp_model {
   // the two halves of the chunk workspaces), so the ramp-up of one chunk's kernels fills the tails of the other's
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_basis = nullptr, ev_aux_done = nullptr, ev_main_done = nullptr;
-  // opt-in stage-parallel host pipeline (VPB200_HOST_PIPE=1, sequence.cu): a high-priority stream for K1/K3/K4 in
-  // chunk order, the vertex kernel of the next chunk underneath on aux_stream; created on first use
-  cudaStream_t hi_stream = nullptr;
-  cudaEvent_t ev_k2[2] = {nullptr, nullptr}, ev_k3[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 
@@ -152,13 +161,14 @@ struct vp_model {
   // profiling
   bool profiling = false;
   float prof_ms[8] = {0};
+  int prof_launches[8] = {0};   // launches summed into prof_ms, per slot
 
   std::mutex mu;
 };
 
 namespace vp {
 
-enum ProfSlot { kProfBasis = 0, kProfVertex = 1, kProfScatter = 2, kProfResolve = 3, kProfSlots = 4 };
+enum ProfSlot { kProfBasis = 0, kProfVertex = 1, kProfScatter = 2, kProfResolve = 3, kProfFused = 4, kProfSlots = 5 };
 
 // ---- reconstruction (reconstruct.cu) ----------------------------------------------------
 int launch_identity(vp_model* m, const float* id_dev, const float* tex_dev, cudaStream_t st);
@@ -178,5 +188,12 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
 int prepare_frame_constants(vp_model* m, const FrameParams* params_dev, int nframes, int rotate_first, double focal,
                             double center, double image_size, double raster_scale, cudaStream_t st, const void** out);
 size_t frame_constants_stride();
+
+// ---- fused vertex + raster path (fused.cu) ----------------------------------------------
+bool fused_available(const vp_model* m);
+int launch_fused(vp_model* m, const float* disp_dev, int nframes, const void* frame_constants, uint32_t* vcol,
+                 unsigned long long* keys, uint32_t epoch, int res, cudaStream_t st);
+int launch_resolve_vcol(const vp_model* m, const unsigned long long* keys, const uint32_t* vcol, uint32_t epoch,
+                        unsigned char* image, unsigned char* mask, int nframes, int h, int w, cudaStream_t st);
 
 }  // namespace vp

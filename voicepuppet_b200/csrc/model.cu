@@ -61,6 +61,9 @@ void free_model(vp_model* m) {
   cudaFree(m->halo);
   cudaFree(m->ring);
   cudaFree(m->fan);
+  cudaFree(m->own_tri_off);
+  cudaFree(m->own_ltri);
+  cudaFree(m->tri_by_orig);
   cudaFree(m->slot_off);
   cudaFree(m->slot_tab);
   cudaFree(m->fan_slot);
@@ -87,9 +90,6 @@ void free_model(vp_model* m) {
   for (cudaEvent_t e : {m->ev_fork, m->ev_basis, m->ev_aux_done, m->ev_main_done})
     if (e) cudaEventDestroy(e);
   if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
-  if (m->hi_stream) cudaStreamDestroy(m->hi_stream);
-  for (cudaEvent_t e : {m->ev_k2[0], m->ev_k2[1], m->ev_k3[0], m->ev_k3[1]})
-    if (e) cudaEventDestroy(e);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   (void)cudaGetLastError();
   delete m;
@@ -172,6 +172,14 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
   VP_TRY(upload(&m->halo, m->topo.halo));
   VP_TRY(upload(&m->ring, m->topo.ring));
   VP_TRY(upload(&m->fan, m->topo.fan));
+  VP_TRY(upload(&m->own_tri_off, m->topo.own_tri_off));
+  VP_TRY(upload(&m->own_ltri, m->topo.own_ltri));
+  {
+    int* t4 = nullptr;
+    VP_TRY(upload(&t4, m->topo.tri_by_orig));
+    m->tri_by_orig = reinterpret_cast<int4*>(t4);
+  }
+  m->fused_ok = m->topo.fused_ok && nver > 0 && ntri > 0;
   if (with_slots) {
     VP_TRY(upload(&m->slot_off, m->topo.slot_off));
     VP_TRY(upload(&m->slot_tab, m->topo.slot_tab));
@@ -245,6 +253,16 @@ extern "C" int vp_set_basis_mode(vp_model* m, int mode) {
   m->basis_mode = mode;
   return VP_OK;
 }
+
+extern "C" int vp_set_raster_path(vp_model* m, int mode) {
+  VP_REQUIRE(m != nullptr, "null model");
+  VP_REQUIRE(mode == 0 || mode == 1, "raster path must be 0 (fused when available) or 1 (separate kernels)");
+  std::lock_guard<std::mutex> lock(m->mu);
+  m->fused_mode = mode;
+  return VP_OK;
+}
+
+extern "C" int vp_model_fused_available(const vp_model* m) { return (m && m->fused_ok) ? 1 : 0; }
 
 extern "C" int vp_set_vertex_mode(vp_model* m, int mode) {
   VP_REQUIRE(m != nullptr, "null model");

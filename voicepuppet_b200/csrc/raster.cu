@@ -54,12 +54,18 @@ int epoch_tri_bits(int ntri) {
 }
 uint32_t epoch_limit(int ntri) { return (1u << (32 - epoch_tri_bits(ntri))) - 1u; }  // largest usable epoch
 
-static EpochKey make_epoch_key(int ntri, uint32_t epoch) {
+EpochKey make_epoch_key(int ntri, uint32_t epoch) {
   EpochKey km;
   km.tri_bits = epoch_tri_bits(ntri);
   km.tri_mask = (1u << km.tri_bits) - 1u;
   km.epoch_field = static_cast<unsigned long long>(epoch) << (32 + km.tri_bits);
   return km;
+}
+
+// Boxes up to this many pixels are walked by their own lane; larger ones are flattened over the warp (raster_walk.cuh).
+int inline_box_pixels() {
+  static const int v = [] { const char* e = std::getenv("VPB200_INLINE_BOX"); return e ? std::atoi(e) : 12; }();
+  return v;
 }
 
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
@@ -89,6 +95,7 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
     a.frames_per_block = fpb;
     a.h = h;
     a.w = w;
+    a.inline_max = inline_box_pixels();
     static const int minb = [] { const char* e = std::getenv("VPB200_SCATTER_MINB"); return e ? std::atoi(e) : 5; }();  // 48 registers, 40 warps/SM: +3 % over 64 / 32
     if (minb >= 6)
       raster_scatter_packed_kernel<6><<<grid, kRasterBlock, 0, st>>>(a);

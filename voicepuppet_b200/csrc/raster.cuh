@@ -10,6 +10,8 @@
 
 #include <cuda_runtime.h>
 
+#include "raster_keys.cuh"
+#include "raster_walk.cuh"
 #include "vp_math.cuh"
 
 namespace vp {
@@ -59,24 +61,6 @@ struct PackedMesh {
     y = v.y;
     z = v.z;
     rgba = __float_as_uint(v.w);
-  }
-};
-
-// Key flavours.  FullKey: 32-bit depth code | 32-bit inverted triangle index, compared against keys
-// initialised from the caller's depth buffer (the mesh_core_cython entry points).  EpochKey: the
-// fused pipeline's variant -- [epoch | depth code | inverted index in `tri_bits` bits]; a key
-// written by an earlier chunk carries a smaller epoch and loses every atomicMax, so the z-buffer
-// never has to be cleared between chunks (the resolve pass treats a stale epoch as background).
-struct FullKey {
-  __device__ __forceinline__ unsigned long long make(float d, uint32_t tri) const { return make_key(d, tri); }
-};
-struct EpochKey {
-  unsigned long long epoch_field;  // epoch << (32 + tri_bits)
-  uint32_t tri_mask;               // (1 << tri_bits) - 1
-  int tri_bits;
-  __device__ __forceinline__ unsigned long long make(float d, uint32_t tri) const {
-    return epoch_field | (static_cast<unsigned long long>(depth_code(d)) << tri_bits) |
-           static_cast<unsigned long long>(tri_mask - tri);
   }
 };
 
@@ -213,22 +197,13 @@ struct ScatterArgs {
   EpochKey km;
   unsigned stride;              // float4 per frame
   int ntri, nframes, frames_per_block, h, w;
+  int inline_max;               // boxes up to this many pixels are walked by their own lane, larger ones flattened
 };
-
-// (a + b + c) / 3 per byte lane of three packed RGBx words; sums <= 765, so x * 0x5556 >> 16 == x / 3.
-__device__ __forceinline__ uint32_t flat_color_packed(uint32_t a, uint32_t b, uint32_t c) {
-  const uint32_t rb = (a & 0x00FF00FFu) + (b & 0x00FF00FFu) + (c & 0x00FF00FFu);  // R | B << 16 (10 bits each)
-  const uint32_t g = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu);
-  const uint32_t r3 = ((rb & 0xFFFFu) * 0x5556u) >> 16;
-  const uint32_t b3 = ((rb >> 16) * 0x5556u) & 0xFFFF0000u;
-  const uint32_t g3 = ((g * 0x5556u) >> 8) & 0xFF00u;
-  return r3 | g3 | b3 | 0xFF000000u;
-}
 
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(kRasterBlock, MIN_BLOCKS)
 raster_scatter_packed_kernel(const ScatterArgs a) {
-  __shared__ Candidate s_big[kRasterBlock / 32];
+  __shared__ float4 s_rec[kRasterBlock / 32][4][32];  // per-warp staging of the flattened large boxes (raster_walk.cuh)
   const int f = blockIdx.x * kRasterBlock + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   const bool valid = f < a.ntri;
@@ -280,54 +255,7 @@ raster_scatter_packed_kernel(const ScatterArgs a) {
       }
     }
 
-    if (c.n > 0 && c.n <= kSmallBox) {
-      // one flat loop over the box: row terms are refreshed when x wraps
-      int x = c.s.x_lo, y = c.s.y_lo;
-      float py = VP_SUB(static_cast<float>(y), c.s.ay);
-      float m0y = VP_MUL(c.s.e0y, py), m1y = VP_MUL(c.s.e1y, py);
-      unsigned long long* row = keys + (unsigned)y * (unsigned)a.w;
-#pragma unroll 1
-      for (int i = 0; i < c.n; ++i) {
-        const float px = VP_SUB(static_cast<float>(x), c.s.ax);
-        const float d02 = VP_ADD(VP_MUL(c.s.e0x, px), m0y);
-        const float d12 = VP_ADD(VP_MUL(c.s.e1x, px), m1y);
-        const float u = VP_MUL(VP_SUB(VP_MUL(c.s.d11, d02), VP_MUL(c.s.d01, d12)), c.s.inv);
-        const float v = VP_MUL(VP_SUB(VP_MUL(c.s.d00, d12), VP_MUL(c.s.d01, d02)), c.s.inv);
-        if (uv_inside(u, v)) atomicMax(row + x, c.key);
-        if (++x > c.s.x_hi) {
-          x = c.s.x_lo;
-          ++y;
-          py = VP_SUB(static_cast<float>(y), c.s.ay);
-          m0y = VP_MUL(c.s.e0y, py);
-          m1y = VP_MUL(c.s.e1y, py);
-          row += a.w;
-        }
-      }
-    }
-    unsigned big = __ballot_sync(0xFFFFFFFFu, c.n > kSmallBox);
-    if (big) {
-      FullKey unused{};
-      Candidate* slot = &s_big[threadIdx.x >> 5];
-      while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        __syncwarp();
-        if ((int)lane == src) *slot = c;
-        __syncwarp();
-        const Candidate o = *slot;
-        const int bw = o.s.x_hi - o.s.x_lo + 1;
-        if (bw >= 16) {  // wide box: the warp strides along x, row by row
-          for (int y = o.s.y_lo; y <= o.s.y_hi; ++y)
-            offer_span<kModeColors>(o, unused, y, o.s.x_lo + (int)lane, o.s.x_hi, 32, keys, a.h, a.w);
-        } else {         // narrow box: 32 / bw' rows at a time (bw' = bw rounded up to a power of two)
-          const int bwp = bw <= 1 ? 1 : (bw <= 2 ? 2 : (bw <= 4 ? 4 : (bw <= 8 ? 8 : 16)));
-          const int rows_per_iter = 32 / bwp;
-          const int dx = (int)lane & (bwp - 1), dy = (int)lane / bwp;
-          for (int y = o.s.y_lo + dy; y <= o.s.y_hi; y += rows_per_iter)
-            if (dx < bw) offer_span<kModeColors>(o, unused, y, o.s.x_lo + dx, o.s.x_lo + dx, 1, keys, a.h, a.w);
-        }
-      }
-    }
+    walk_boxes(c.s, c.key, c.n, a.inline_max, s_rec[threadIdx.x >> 5], keys, a.w, lane);
   }
 }
 

@@ -28,7 +28,8 @@ size_t env_size(const char* name, size_t dflt) {
 // host-output path cuts the sequence into at least four chunks so that the device->host drain of one
 // chunk overlaps the rendering of the next.  Chunks are equal-sized so that no launch runs nearly empty.
 int chunk_frames(const vp_model* m, int res, int nframes, bool host_outputs) {
-  const size_t per_frame = (size_t)m->vrec_stride * 16 + (size_t)res * res * 8 + (size_t)m->ntri * 4;
+  const size_t per_frame = fused_available(m) ? (size_t)m->vrec_stride * 4 + (size_t)res * res * 8
+                                              : (size_t)m->vrec_stride * 16 + (size_t)res * res * 8 + (size_t)m->ntri * 4;
   const size_t forced = env_size("VPB200_CHUNK_FRAMES", 0);
   size_t c = forced ? forced : (env_size("VPB200_CHUNK_MB", 192) << 20) / per_frame;
   c = std::max<size_t>(c, 4);
@@ -39,7 +40,7 @@ int chunk_frames(const vp_model* m, int res, int nframes, bool host_outputs) {
   size_t nchunks = std::max<size_t>(1, (t * 10 + c * 11 - 1) / (c * 11));  // ceil(t / (1.1 c))
   // two chunks on the two streams of ChunkRunner beat one large launch sequence (75 frames at 256x256: 149 vs
   // 156 us): the second chunk's kernels fill the tails of the first's
-  if (!host_outputs && nchunks == 1 && t >= 48 && !m->profiling) nchunks = 2;  // per-kernel profiling times whole launches
+  if (!host_outputs && nchunks == 1 && t >= 48) nchunks = 2;  // (profiling keeps the same chunks, on one stream)
   return (int)((t + nchunks - 1) / nchunks);
 }
 
@@ -64,10 +65,16 @@ struct Profiler {
   void finish() {
     if (!m->profiling) return;
     cudaStreamSynchronize(st);
-    for (int k = 0; k < kProfSlots; ++k) m->prof_ms[k] = 0.f;
+    for (int k = 0; k < kProfSlots; ++k) {
+      m->prof_ms[k] = 0.f;
+      m->prof_launches[k] = 0;
+    }
     for (const Span& s : spans) {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) m->prof_ms[s.slot] += ms;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+        m->prof_ms[s.slot] += ms;
+        ++m->prof_launches[s.slot];
+      }
       cudaEventDestroy(s.a);
       cudaEventDestroy(s.b);
     }
@@ -99,7 +106,7 @@ struct ChunkRunner {
   const float* ex_dev = nullptr;
   const FrameParams* params_dev = nullptr;
   const char* fconst = nullptr;
-  bool dual = false, aux_used = false, aux_needs_basis = false;
+  bool dual = false, aux_used = false, aux_needs_basis = false, fused = false;
   int issued = 0;
 
   ChunkRunner(vp_model* m_, cudaStream_t st_) : m(m_), st(st_), prof(m_, st_) {}
@@ -114,18 +121,26 @@ struct ChunkRunner {
     rotate_first = rotate_first_;
     group = basis_group_frames(chunk_cap, nframes);
     static const int dual_env = [] { const char* e = std::getenv("VPB200_DUAL"); return e ? std::atoi(e) : 1; }();
-    dual = allow_dual && dual_env != 0 && nchunks >= 2 && !m->profiling && (uint32_t)nchunks + 4u < epoch_limit(m->ntri);
+    // one z-buffer epoch per run() call: a planned chunk that crosses a basis group or exceeds 1024 frames takes
+    // several, so budget for the worst case (and run() refuses to go past the limit)
+    const uint32_t launches_max = (uint32_t)nchunks + (uint32_t)(nframes / std::max(group, 1)) + (uint32_t)(nframes / 1024) + 4u;
+    dual = allow_dual && dual_env != 0 && nchunks >= 2 && !m->profiling && launches_max + 2u < epoch_limit(m->ntri);
+    fused = fused_available(m);
     const int slots = dual ? 2 : 1;
     const size_t npix = (size_t)res * res;
     VP_CUDA(m->ws_disp.reserve((size_t)group * m->rows_pad * sizeof(float), m->device));  // >= any group
-    VP_CUDA(m->ws_vrec.reserve((size_t)slots * chunk_cap * m->vrec_stride * sizeof(float4), m->device));
-    VP_CUDA(m->ws_tricol.reserve((size_t)slots * chunk_cap * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
+    if (fused) {
+      VP_CUDA(m->ws_vcol.reserve((size_t)slots * chunk_cap * m->vrec_stride * sizeof(uint32_t), m->device));
+    } else {
+      VP_CUDA(m->ws_vrec.reserve((size_t)slots * chunk_cap * m->vrec_stride * sizeof(float4), m->device));
+      VP_CUDA(m->ws_tricol.reserve((size_t)slots * chunk_cap * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
+    }
     void* before = m->ws_keys.ptr;
     VP_CUDA(m->ws_keys.reserve((size_t)slots * chunk_cap * npix * sizeof(unsigned long long), m->device));
     if (m->ws_keys.ptr != before) m->key_epoch = 0;
     // every chunk gets a fresh epoch; stale keys lose every atomicMax and read as background.  The z-buffer is
     // cleared only when the epoch counter would wrap during this call (or the buffer is new)
-    if (m->key_epoch == 0 || m->key_epoch + (uint32_t)nchunks + 2u >= epoch_limit(m->ntri)) {
+    if (m->key_epoch == 0 || m->key_epoch + launches_max + 2u >= epoch_limit(m->ntri)) {
       VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
       m->key_epoch = 0;
     }
@@ -161,8 +176,22 @@ struct ChunkRunner {
       aux_needs_basis = false;
     }
     ++issued;
+    VP_REQUIRE(m->key_epoch + 1u <= epoch_limit(m->ntri), "z-buffer epoch counter exhausted (more launches than budgeted)");
     const uint32_t epoch = ++m->key_epoch;
     const size_t npix = (size_t)res * res;
+    if (fused) {
+      uint32_t* vcol = m->ws_vcol.as<uint32_t>() + (size_t)slot * chunk_cap * m->vrec_stride;
+      unsigned long long* fkeys = m->ws_keys.as<unsigned long long>() + (size_t)slot * chunk_cap * npix;
+      const float* fdisp = ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr;
+      prof.begin(kProfFused);
+      VP_TRY(launch_fused(m, fdisp, n, fconst + (size_t)t0 * frame_constants_stride(), vcol, fkeys, epoch, res, cs));
+      prof.end();
+      prof.begin(kProfResolve);
+      VP_TRY(launch_resolve_vcol(m, fkeys, vcol, epoch, image_dev, mask_dev, n, res, res, cs));
+      prof.end();
+      if (used) *used = cs;
+      return VP_OK;
+    }
     float4* vrec = m->ws_vrec.as<float4>() + (size_t)slot * chunk_cap * m->vrec_stride;
     unsigned long long* keys = m->ws_keys.as<unsigned long long>() + (size_t)slot * chunk_cap * npix;
     uint32_t* tricol = m->ws_tricol.as<uint32_t>() + (size_t)slot * chunk_cap * std::max(m->ntri, 1);
@@ -199,95 +228,6 @@ struct ChunkRunner {
     return rc;
   }
 };
-
-// Opt-in (VPB200_HOST_PIPE=1) host-output pipeline, stage-parallel instead of chunk-parallel: the chunks keep their
-// order on a high-priority stream (K1, then K3 and K4 of every chunk, each followed by its device->host copy on
-// the copy stream) while the vertex kernel of the NEXT chunk runs underneath on the low-priority auxiliary stream.
-// K2 is bound by the LSU data pipe and K3 by instruction issue, so they share an SM well, and unlike two whole
-// chunks in flight this does not delay the first chunk, which is what the PCIe drain waits for.  Written from the
-// round-1 measurements (per-chunk 68 us against 67 us of drain per 19 frames); not yet measured on the GPU.
-int render_host_pipelined(vp_model* m, int T, int res, int chunk, int first, const float* ex_dev,
-                          const FrameParams* params_dev, int rotate_first, unsigned char* image, unsigned char* face_mask,
-                          cudaStream_t st) {
-  if (!m->hi_stream) {
-    int least = 0, greatest = 0;
-    VP_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    VP_CUDA(cudaStreamCreateWithPriority(&m->hi_stream, cudaStreamNonBlocking, greatest));
-    for (int i = 0; i < 2; ++i) {
-      VP_CUDA(cudaEventCreateWithFlags(&m->ev_k2[i], cudaEventDisableTiming));
-      VP_CUDA(cudaEventCreateWithFlags(&m->ev_k3[i], cudaEventDisableTiming));
-    }
-  }
-  cudaStream_t H = m->hi_stream, L = m->aux_stream;
-  const size_t npix = (size_t)res * res;
-  const int group = basis_group_frames(chunk, T);
-  const int nchunks_est = 4 + (T + chunk - 1) / chunk + T / 96;
-  // workspaces: two vertex-record slots (K2 of chunk c+1 writes one while K3 of chunk c reads the other)
-  VP_CUDA(m->ws_disp.reserve((size_t)group * m->rows_pad * sizeof(float), m->device));
-  VP_CUDA(m->ws_vrec.reserve((size_t)2 * chunk * m->vrec_stride * sizeof(float4), m->device));
-  VP_CUDA(m->ws_tricol.reserve((size_t)2 * chunk * std::max(m->ntri, 1) * sizeof(uint32_t), m->device));
-  void* before = m->ws_keys.ptr;
-  VP_CUDA(m->ws_keys.reserve((size_t)2 * chunk * npix * sizeof(unsigned long long), m->device));
-  if (m->ws_keys.ptr != before) m->key_epoch = 0;
-  if (m->key_epoch == 0 || m->key_epoch + (uint32_t)nchunks_est + 2u >= epoch_limit(m->ntri)) {
-    VP_CUDA(cudaMemsetAsync(m->ws_keys.ptr, 0, m->ws_keys.cap, st));
-    m->key_epoch = 0;
-  }
-  for (int b = 0; b < 2; ++b) {
-    VP_CUDA(m->ws_img[b].reserve((size_t)chunk * npix * 3, m->device));
-    if (face_mask) VP_CUDA(m->ws_mask[b].reserve((size_t)chunk * npix, m->device));
-  }
-  const void* fc = nullptr;
-  VP_TRY(prepare_frame_constants(m, params_dev, T, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, st, &fc));
-  const char* fconst = static_cast<const char*>(fc);
-  VP_CUDA(cudaEventRecord(m->ev_fork, st));       // uploads, frame constants, z-buffer clear: before anything below
-  VP_CUDA(cudaStreamWaitEvent(H, m->ev_fork, 0));
-  VP_CUDA(cudaStreamWaitEvent(L, m->ev_fork, 0));
-  ReconOut none;
-  int ci = 0;
-  for (int t0 = 0, n = 0; t0 < T; t0 += n, ++ci) {
-    n = std::min(std::min(t0 == 0 ? first : chunk, T - t0), group - t0 % group);
-    const int slot = ci & 1;
-    if (ex_dev && t0 % group == 0) {              // K1 of the group on H (after K3/K4 of the previous group's chunks)
-      if (ci > 0) VP_CUDA(cudaStreamWaitEvent(H, m->ev_k2[(ci - 1) & 1], 0));  // its last K2 has read ws_disp
-      VP_TRY(launch_basis(m, ex_dev + (size_t)t0 * VP_N_EX, m->ws_disp.as<float>(), std::min(group, T - t0), H));
-      VP_CUDA(cudaEventRecord(m->ev_basis, H));
-      VP_CUDA(cudaStreamWaitEvent(L, m->ev_basis, 0));
-    }
-    float4* vrec = m->ws_vrec.as<float4>() + (size_t)slot * chunk * m->vrec_stride;
-    unsigned long long* keys = m->ws_keys.as<unsigned long long>() + (size_t)slot * chunk * npix;
-    uint32_t* tricol = m->ws_tricol.as<uint32_t>() + (size_t)slot * chunk * std::max(m->ntri, 1);
-    const float* disp = ex_dev ? m->ws_disp.as<float>() + (size_t)(t0 % group) * m->rows_pad : nullptr;
-    // ---- K2 of this chunk on L, once K3 of chunk ci - 2 no longer reads this slot's vertex records ----------------
-    if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(L, m->ev_k3[slot], 0));
-    VP_TRY(launch_vertex(m, disp, params_dev + t0, n, rotate_first, 1015.0, 112.0, 224.0, (double)res / 224.0, vrec, none,
-                         L, fconst + (size_t)t0 * frame_constants_stride()));
-    VP_CUDA(cudaEventRecord(m->ev_k2[slot], L));
-    // ---- K3, K4 on H in chunk order, then the drain -----------------------------------------------------------------
-    VP_CUDA(cudaStreamWaitEvent(H, m->ev_k2[slot], 0));
-    if (ci >= 2) VP_CUDA(cudaStreamWaitEvent(H, m->ev_copy[slot], 0));   // staging image of chunk ci - 2 has drained
-    const uint32_t epoch = ++m->key_epoch;
-    VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, epoch, n, m->ntri, res, res, H));
-    VP_CUDA(cudaEventRecord(m->ev_k3[slot], H));
-    unsigned char* img = m->ws_img[slot].as<unsigned char>();
-    unsigned char* msk = face_mask ? m->ws_mask[slot].as<unsigned char>() : nullptr;
-    VP_TRY(launch_resolve_packed(keys, tricol, m->t_orig2int_dev, epoch, img, msk, n, m->ntri, res, res, H));
-    VP_CUDA(cudaEventRecord(m->ev_render[slot], H));
-    VP_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_render[slot], 0));
-    VP_CUDA(cudaMemcpyAsync(image + (size_t)t0 * npix * 3, img, (size_t)n * npix * 3, cudaMemcpyDeviceToHost, m->copy_stream));
-    if (face_mask)
-      VP_CUDA(cudaMemcpyAsync(face_mask + (size_t)t0 * npix, msk, (size_t)n * npix, cudaMemcpyDeviceToHost, m->copy_stream));
-    VP_CUDA(cudaEventRecord(m->ev_copy[slot], m->copy_stream));
-  }
-  // join everything back onto the caller's stream, then wait (the call returns frames in host memory)
-  VP_CUDA(cudaEventRecord(m->ev_main_done, H));
-  VP_CUDA(cudaStreamWaitEvent(st, m->ev_main_done, 0));
-  VP_CUDA(cudaEventRecord(m->ev_aux_done, L));
-  VP_CUDA(cudaStreamWaitEvent(st, m->ev_aux_done, 0));
-  VP_CUDA(cudaStreamSynchronize(st));
-  VP_CUDA(cudaStreamSynchronize(m->copy_stream));
-  return VP_OK;
-}
 
 int check_sequence_args(const vp_model* m, int nframes, int res, const void* image) {
   VP_REQUIRE(m != nullptr, "null model");
@@ -446,19 +386,6 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
   // matters is how soon it starts: the first chunk is short, the following ones full-sized.
   const int first = (outputs_on_device || forced_chunk || T < 4 * 8) ? chunk : std::max(6, chunk / 3);
   const int nchunks_est = 2 + (T + chunk - 1) / chunk + T / 96;
-  static const int host_pipe = [] { const char* e = std::getenv("VPB200_HOST_PIPE"); return e ? std::atoi(e) : 0; }();
-  if (host_pipe && !outputs_on_device && !m->profiling && T >= 16) {
-    const int rc_pipe = render_host_pipelined(m, T, res, chunk, first, ex_dev, params_dev, fr->rotate_shape_first, image,
-                                              face_mask, st);
-    if (rc_pipe != VP_OK) {
-      m->key_epoch = 0;
-      cudaStreamSynchronize(st);
-      if (m->hi_stream) cudaStreamSynchronize(m->hi_stream);
-      cudaStreamSynchronize(m->aux_stream);
-      cudaStreamSynchronize(m->copy_stream);
-    }
-    return rc_pipe;
-  }
   ChunkRunner run(m, st);
   // host outputs: the PCIe drain is the slow side and wants the FIRST chunk as early as possible, which two
   // chunks in flight delay (measured: 454 vs 417 us per 75-frame call), so that path stays on one stream
@@ -536,10 +463,17 @@ extern "C" int vp_set_profiling(vp_model* m, int enabled) {
   return VP_OK;
 }
 
+extern "C" int vp_get_profile_launches(vp_model* m, int* launches, int cap) {
+  VP_REQUIRE(m != nullptr && launches != nullptr, "null argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  for (int k = 0; k < kProfSlots && k < cap; ++k) launches[k] = m->prof_launches[k];
+  return VP_OK;
+}
+
 extern "C" int vp_get_profile(vp_model* m, char* names, int names_cap, float* ms, int ms_cap) {
   VP_REQUIRE(m != nullptr, "null model");
   std::lock_guard<std::mutex> lock(m->mu);
-  static const char kNames[] = "basis;vertex;scatter;resolve";
+  static const char kNames[] = "basis;vertex;scatter;resolve;fused";
   if (names && names_cap > 0) {
     std::snprintf(names, (size_t)names_cap, "%s", kNames);
   }

@@ -200,6 +200,17 @@ int build_topology(Topology& out, int nver, int ntri, const int* tri, const int*
     out.tri_int[4 * (size_t)i + 3] = f;
   }
 
+  // first tri_int row whose smallest vertex is >= v (rows are sorted by it)
+  std::vector<int> first_row(nver + 1, ntri);
+  for (int i = ntri - 1; i >= 0; --i) first_row[t_key[t_order[i]]] = i;
+  for (int iv = nver - 1; iv >= 0; --iv) first_row[iv] = std::min(first_row[iv], first_row[iv + 1]);
+  out.own_ltri.assign((size_t)ntri, 0u);
+  out.own_tri_off.clear();
+  out.fused_ok = true;
+  out.tri_by_orig.assign((size_t)ntri * 4, 0);
+  for (int f = 0; f < ntri; ++f)
+    for (int c = 0; c < 3; ++c) out.tri_by_orig[4 * (size_t)f + c] = out.v_orig2int[tri[3 * (size_t)f + c]];
+
   // ---- vertex tiles ----------------------------------------------------------------------
   out.ring.assign((size_t)nver * VP_RING, kRingPad);
   out.fan.assign((size_t)nver * kFanWords, 0u);
@@ -332,8 +343,21 @@ int build_topology(Topology& out, int nver, int ntri, const int* tri, const int*
       const uint32_t c = (uint32_t)ver_local[out.v_orig2int[tri[3 * (size_t)f + 2]]];
       out.ltri.push_back(a | (b << 10) | (c << 20));
     }
+    // ---- owned triangles (fused kernel): corners in this tile's local numbering --------------
+    out.own_tri_off.push_back(first_row[td.v_begin]);
+    for (int i = first_row[td.v_begin]; i < first_row[td.v_begin + td.nv]; ++i) {
+      uint32_t packed = 0;
+      for (int c = 0; c < 3; ++c) {
+        const int iv = out.tri_int[4 * (size_t)i + c];
+        if (ver_stamp[iv] != tile_id) out.fused_ok = false;  // a corner the tile never staged (inconsistent point_buf)
+        else packed |= (uint32_t)ver_local[iv] << (10 * c);
+      }
+      out.own_ltri[i] = packed;
+    }
+    if (!td.fan || first_row[td.v_begin + td.nv] - first_row[td.v_begin] > kTileLT) out.fused_ok = false;
     out.tiles.push_back(td);
   }
+  out.own_tri_off.push_back(ntri);
   if (with_slots) assign_slots(out);
   return VP_OK;
 }
@@ -381,6 +405,17 @@ extern "C" int vp_topology_copy(const vp_topology* h, int* v_int2orig, int* tri_
   if (ring) std::memcpy(ring, t.ring.data(), t.ring.size() * sizeof(uint16_t));
   if (fan) std::memcpy(fan, t.fan.data(), t.fan.size() * sizeof(uint32_t));
   return VP_OK;
+}
+
+/* Triangle ownership of the fused vertex + raster kernel: own_tri_off[ntiles + 1], own_ltri[ntri],
+ * tri_by_orig[ntri][4]; returns 1 when the fused kernel can take the mesh, 0 when it cannot, < 0 on error. */
+extern "C" int vp_topology_copy_owned(const vp_topology* h, int* own_tri_off, uint32_t* own_ltri, int* tri_by_orig) {
+  if (h == nullptr) return VP_ERR_ARG;
+  const vp::Topology& t = h->t;
+  if (own_tri_off) std::memcpy(own_tri_off, t.own_tri_off.data(), t.own_tri_off.size() * sizeof(int));
+  if (own_ltri) std::memcpy(own_ltri, t.own_ltri.data(), t.own_ltri.size() * sizeof(uint32_t));
+  if (tri_by_orig) std::memcpy(tri_by_orig, t.tri_by_orig.data(), t.tri_by_orig.size() * sizeof(int));
+  return t.fused_ok ? 1 : 0;
 }
 
 /* The optional slot tables (always built by vp_topology_build): slot_off[ntiles] (-1 = generic tile),

@@ -244,3 +244,13 @@ class DeviceModel(object):
     _lib.check(_lib.lib().vp_get_profile(self.handle, names, 256, _lib.ptr(ms), 8))
     keys = names.value.decode().split(';')
     return dict(zip(keys, [float(x) for x in ms[:len(keys)]]))
+
+  def profile_launches(self):
+    """Kernel launches behind every entry of profile() (same keys)."""
+    names = ctypes.create_string_buffer(256)
+    ms = np.zeros(8, dtype=np.float32)
+    _lib.check(_lib.lib().vp_get_profile(self.handle, names, 256, _lib.ptr(ms), 8))
+    counts = np.zeros(8, dtype=np.int32)
+    _lib.check(_lib.lib().vp_get_profile_launches(self.handle, _lib.ptr(counts), 8))
+    keys = names.value.decode().split(';')
+    return dict(zip(keys, [int(x) for x in counts[:len(keys)]]))

@@ -266,8 +266,8 @@ class Env(object):
     self.model = synthetic.cached_model()
     self.dm = DeviceModel.of(self.model, self.local_rank)
     self.lib = _lib.lib()
-    if os.environ.get('VPB200_BENCH_SEPARATE') == '1':     # A/B: the separate vertex / scatter / resolve kernels
-      _lib.check(self.lib.vp_set_raster_path(self.dm.handle, 1))
+    if os.environ.get('VPB200_BENCH_FUSED') == '1':        # A/B: the fused vertex + z-buffer kernel (not the default)
+      _lib.check(self.lib.vp_set_raster_path(self.dm.handle, 2))
     self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)       # > 126 MB L2
     self.flush_src = torch.zeros(64 << 20, dtype=torch.float32, device=self.dev)  # 256 MiB read pass
     self.flush_mode = os.environ.get('VPB200_FLUSH', 'write+read')
@@ -616,7 +616,8 @@ def run_sharded(env, name, steps, warmup):
                           'under the rendering of the next chunk; device-side completion flags' if peer is not None
                           else 'NCCL gather of uint8 frames to rank 0, per chunk on a side stream'),
                  'rank0_ingest_bytes_per_step': ingest, 'render_only_ms': render_ms, 'exposed_gather_ms': exposed_ms,
-                 'rank0_ingest_gbs_over_step': round(ingest / ms_per_step / 1e6, 1)},
+                 'rank0_ingest_gbs_over_step': round(ingest / ms_per_step / 1e6, 1),
+                 'completion_wait_timeouts': int(lib.vp_peer_timeouts())},
       'e2e': {'value': frames / e2e_sec, 'unit': 'frames/s',
               'h2d_bytes_per_step': frames * (64 * 4 + 192), 'd2h_bytes_per_step': world * per * frame_bytes,
               'note': 'every rank uploads its coefficient rows, renders and pushes; rank 0 then drains the gathered '

@@ -75,6 +75,9 @@ int vp_ipc_close(void* base);
  * traps after a bounded spin instead of hanging).  Use an increasing step counter as `value`. */
 int vp_peer_signal(unsigned int* flag_dev, unsigned int value, void* stream);
 int vp_peer_wait(const unsigned int* flags_dev, int n, unsigned int value, void* stream);
+/* A wait gives up after VPB200_PEER_TIMEOUT_S seconds (default 60) instead of hanging the GPU; this returns how many
+ * waits on the current device gave up since the library was loaded (check it after synchronising), < 0 on error. */
+int vp_peer_timeouts(void);
 /* Asynchronous device-to-device copy (copy engine), e.g. finished frames -> the peer-mapped buffer. */
 int vp_copy_async(void* dst_dev, const void* src_dev, size_t bytes, void* stream);
 
@@ -160,7 +163,7 @@ int vp_topology_sizes(const vp_topology* t, int* ntiles, int* nltri, int* nhalo)
 int vp_topology_copy(const vp_topology* t, int* v_int2orig, int* tri_int, int* tiles, uint32_t* ltri,
                      int* halo, uint16_t* ring, uint32_t* fan);
 /* Optional bank-conflict-aware shared-memory slots of the fan tiles (used by the vertex kernel when the model was
- * created with VPB200_VERTEX_SLOTS=1): slot_off[ntiles] (offset into slot_tab, -1 for generic tiles),
+ * always built): slot_off[ntiles] (offset into slot_tab, -1 for generic tiles),
  * slot_tab[vp_topology_slot_count()] (slot of local vertex i), fan_slot[nver][5] (fan records in slot space). */
 /* Triangle ownership of the fused vertex + raster kernel (csrc/fused.cu): tile i owns rows
  * own_tri_off[i] .. own_tri_off[i + 1] of tri_int (the triangles whose smallest internal vertex it holds);
@@ -204,16 +207,18 @@ int vp_expression_loss_dev(vp_model* m, const float* delta_ex_dev, const int* se
  * tcgen05 3xTF32 GEMM from 16 frames up), 1 = always FP32 SIMT, 2 = always tcgen05 3xTF32. */
 int vp_set_basis_mode(vp_model* m, int mode);
 
-/* Vertex-normal path selection: 0 = automatic (fan records where the mesh chains into fans, the generic
- * ring-of-faces kernel elsewhere), 1 = always the generic kernel (tests compare the two). */
+/* Vertex-normal path selection: 0 = automatic (fan records where the mesh chains into fans, positions staged at
+ * bank-conflict-aware shared-memory slots; the generic ring-of-faces kernel elsewhere), 1 = always the generic
+ * kernel, 2 = fan records with the identity slot placement (tests compare the three). */
 int vp_set_vertex_mode(vp_model* m, int mode);
 int vp_model_fan_tiles(const vp_model* m); /* tiles that take the fan path (of vp_model_ntiles) */
 
-/* Chunk pipeline of vp_render_sequence*: 0 = automatic -- the fused vertex + z-buffer kernel (csrc/fused.cu: one
- * CTA per vertex tile projects its vertices and rasterizes the triangles it owns out of shared memory) whenever
- * every tile has fan records and every triangle's corners are local to its owner tile (any manifold mesh with a
- * consistent point_buf: vp_model_fused_available() == 1); 1 = always the separate kernels (vertex records ->
- * scatter -> resolve), which the tests compare it with bit for bit. */
+/* Chunk pipeline of vp_render_sequence*: 0 = automatic (the measured best: today the separate kernels, vertex
+ * records -> scatter -> resolve, at every size), 1 = always the separate kernels, 2 = the fused vertex + z-buffer
+ * kernel (csrc/fused.cu: one CTA per vertex tile projects its own and halo vertices and rasterizes the triangles it
+ * owns out of shared memory; no vertex records, colours resolved from per-vertex colours).  Mode 2 needs every tile
+ * to have fan records and every triangle's corners to be local to its owner tile (any manifold mesh with a
+ * consistent point_buf: vp_model_fused_available() == 1) and is bit-identical to mode 1 (tests). */
 int vp_set_raster_path(vp_model* m, int mode);
 int vp_model_fused_available(const vp_model* m);
 

@@ -166,17 +166,17 @@ def test_fused_kernel_is_bit_identical_to_the_separate_kernels(full_model, res, 
   lib = _lib.lib()
   assert lib.vp_model_fused_available(dm.handle) == 1
   coeffs = synthetic.make_coeffs(frames, seed=11)
-  fused, fused_mask = render.render_sequence(coeffs, full_model, res=res, want_mask=True)
-  fused, fused_mask = np.asarray(fused).copy(), np.asarray(fused_mask).copy()
   dev = torch.empty((frames, res, res, 3), dtype=torch.uint8, device='cuda:0')
-  render.render_sequence(coeffs, full_model, res=res, out=dev)
-  torch.cuda.synchronize()
-  _lib.check(lib.vp_set_raster_path(dm.handle, 1))
+  _lib.check(lib.vp_set_raster_path(dm.handle, 2))
   try:
-    sep, sep_mask = render.render_sequence(coeffs, full_model, res=res, want_mask=True)
-    sep, sep_mask = np.asarray(sep).copy(), np.asarray(sep_mask).copy()
+    fused, fused_mask = render.render_sequence(coeffs, full_model, res=res, want_mask=True)
+    fused, fused_mask = np.asarray(fused).copy(), np.asarray(fused_mask).copy()
+    render.render_sequence(coeffs, full_model, res=res, out=dev)
+    torch.cuda.synchronize()
   finally:
     _lib.check(lib.vp_set_raster_path(dm.handle, 0))
+  sep, sep_mask = render.render_sequence(coeffs, full_model, res=res, want_mask=True)
+  sep, sep_mask = np.asarray(sep).copy(), np.asarray(sep_mask).copy()
   assert fused_mask.any() and np.array_equal(fused_mask, sep_mask)
   assert np.array_equal(fused, sep)
   assert np.array_equal(dev.cpu().numpy(), sep)
@@ -192,7 +192,7 @@ def test_fused_kernel_small_model_and_coefficient_angles(small_model):
   coeffs = synthetic.make_coeffs(7, seed=3)
   for angles in ('jitter', None):
     a = np.asarray(render.render_sequence(coeffs, small_model, res=96, angles=angles)).copy()
-    _lib.check(lib.vp_set_raster_path(dm.handle, 1))
+    _lib.check(lib.vp_set_raster_path(dm.handle, 2))
     try:
       b = np.asarray(render.render_sequence(coeffs, small_model, res=96, angles=angles)).copy()
     finally:

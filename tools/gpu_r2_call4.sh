@@ -2,7 +2,7 @@
 # Round 2, call 4: flattened big-box walk in both raster paths: parity, then separate vs fused x inline threshold.
 mkdir -p gpurun_out
 echo "== parity"
-timeout 900 python -m pytest tests/test_gpu_sequence.py tests/test_gpu_raster.py tests/test_gpu_full_sizes.py -x -q 2>&1 | tail -6
+timeout 900 python -m pytest tests/test_gpu_sequence.py tests/test_gpu_raster.py tests/test_gpu_full_sizes.py tests/test_gpu_reconstruct.py -x -q 2>&1 | tail -6
 b() { timeout 600 python bench.py --steps 4 --warmup 3 --frames $F --res $R --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],3), {k:round(v['ms']*1e3,1) for k,v in d['kernels'].items()})"; }
 for cfg in "75 256" "1500 512" "1024 1024"; do
   set -- $cfg; export F=$1 R=$2

@@ -35,17 +35,31 @@ print('|---|' + '---|' * len(keep))
 for r in data:
   print('| %s | ' % r[idx['Kernel Name']].split('(')[0].split('::')[-1][:40] + ' | '.join('%.2f' % g(r, h, 0) for h in keep) + ' |')
 KERNEL_SLOTS = (('basis_tc_kernel', 'basis'), ('basis_simt_kernel', 'basis'), ('vertex_fan_kernel', 'vertex'),
-                ('vertex_tile_kernel', 'vertex'), ('raster_scatter', 'scatter'), ('resolve_packed_kernel', 'resolve'))
+                ('vertex_tile_kernel', 'vertex'), ('raster_scatter', 'scatter'), ('resolve_packed_kernel', 'resolve'),
+                ('fused_tile_kernel', 'fused'), ('resolve_vcol_kernel', 'resolve'))
 if '--traffic-json' in sys.argv:   # per-launch DRAM traffic of the hot kernels, read back by bench.py
-  import json
+  import json, os
   out_path = sys.argv[sys.argv.index('--traffic-json') + 1]
-  traffic = {'source': rep.split('/')[-1], 'note': 'dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 75 frames at 256x256'}
+  key = sys.argv[sys.argv.index('--key') + 1]          # "<frames>x<res>" of the bench configuration the capture belongs to
+  traffic = {'source': rep.split('/')[-1], 'note': 'dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the captured launches of the kernel), ncu --set full --clock-control none'}
+  sums, counts = {}, {}
   for r in data:
     for pat, slot in KERNEL_SLOTS:
       if pat in r[idx['Kernel Name']]:
-        traffic[slot] = int(scale(r, 'dram__bytes_read.sum') + scale(r, 'dram__bytes_write.sum'))
-  json.dump(traffic, open(out_path, 'w'), indent=1)
-args = [a for a in sys.argv[2:] if not a.startswith('--') and not a.endswith('.json')]
+        sums[slot] = sums.get(slot, 0) + scale(r, 'dram__bytes_read.sum') + scale(r, 'dram__bytes_write.sum')
+        counts[slot] = counts.get(slot, 0) + 1
+  for slot in sums:
+    traffic[slot] = int(sums[slot] / counts[slot])
+  allt = json.load(open(out_path)) if os.path.exists(out_path) else {}
+  if not all(isinstance(v, dict) for v in allt.values()):
+    allt = {}                                            # round-1 layout (one flat dict): start over
+  allt[key] = traffic
+  json.dump(allt, open(out_path, 'w'), indent=1)
+skip = set()
+for flag in ('--traffic-json', '--key'):
+  if flag in sys.argv:
+    skip.add(sys.argv[sys.argv.index(flag) + 1])
+args = [a for a in sys.argv[2:] if not a.startswith('--') and a not in skip]
 if args:
   sys.argv = sys.argv[:2] + args
   lr = list(csv.DictReader(l for l in open(sys.argv[2]) if l.startswith('"')))

@@ -63,6 +63,7 @@ SIGNATURES = {
     'vp_copy_async': (_i, [_vp, _vp, _sz, _vp]),
     'vp_peer_signal': (_i, [_vp, ctypes.c_uint, _vp]),
     'vp_peer_wait': (_i, [_vp, _i, ctypes.c_uint, _vp]),
+    'vp_peer_timeouts': (_i, []),
     'vp_render_colors_core': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i]),
     'vp_rasterize_triangles_core': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     'vp_render_texture_core': (_i, [_vp] * 7 + [_i] * 10),

@@ -38,17 +38,9 @@ constexpr int kStagesL = 2;               // "lo" tiles and TMEM accumulators
 constexpr int kHalfA = kTcM * 128;        // bytes of one K-half (32 floats) of an A tile
 constexpr int kTileA = 2 * kHalfA;        // 32 KB
 constexpr int kOffAhi = 0;
-// Two flavours of the epilogue (template parameter BULK of the kernel):
-//   BULK = false  TMEM -> registers -> 128-byte warp stores, 3-stage TMA ring of A tiles (measured, default)
-//   BULK = true   TMEM -> registers -> a [frame][128 rows] staging tile in shared memory -> one 512-byte TMA bulk
-//                 store per frame (cp.async.bulk shared -> global); the staging tile takes the place of the third
-//                 A stage.  Opt-in (VPB200_BASIS_EPI=1), written from the round-1 CTA timeline that shows the
-//                 epilogue's stores as the per-tile limiter; not yet measured on the GPU.
-__host__ __device__ constexpr int stages_a(bool bulk) { return bulk ? 2 : 3; }   // TMA ring of fp32 A tiles (the "hi" operand in place)
-__host__ __device__ constexpr int off_alo(bool bulk) { return stages_a(bulk) * kTileA; }
-__host__ __device__ constexpr int off_b(bool bulk) { return off_alo(bulk) + kStagesL * kTileA; }  // B hi/lo tiles (1024-byte aligned; size
-                                                                              // depends on the frame count), then the
-                                                                              // staging tile (BULK), then the barriers
+constexpr int kStagesA = 3;               // TMA ring of fp32 A tiles (the "hi" operand in place)
+constexpr int kOffAlo = kStagesA * kTileA;
+constexpr int kOffB = kOffAlo + kStagesL * kTileA;  // B hi/lo tiles (1024-byte aligned; size depends on the frame count), then the barriers
 // warp roles: 0 = TMA producer, 1 = MMA issuer, 2-9 = epilogue (two warps per TMEM lane quarter),
 // 10-17 = operand split
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpEpi0 = 2, kWarpSplit0 = 10;
@@ -57,11 +49,7 @@ constexpr int kTcThreads = (kWarpSplit0 * 32) + kSplitThreads;  // 576
 constexpr int kPrefetchTiles = 4;         // L2 prefetch distance of the TMA producer, in tiles
 constexpr uint32_t kTf32Mask = 0xFFFFE000u;
 
-inline int tc_smem_bytes(int n_mma, bool bulk) { return off_b(bulk) + 2 * n_mma * 256 + (bulk ? n_mma * 512 : 0) + 128; }
-// dynamic shared memory both flavours may ask for: what the default flavour needs for 128 frames (229,504 B, known
-// to be accepted; the opt-in limit of the part is 232,448 B)
-inline int max_dyn_smem() { return tc_smem_bytes(128, false); }
-bool g_bulk_ok = false;
+inline int tc_smem_bytes(int n_mma) { return kOffB + 2 * n_mma * 256 + 128; }
 
 // 3xTF32 split by truncation: hi keeps the 19 bits the tensor core reads, lo = x - hi is exact in fp32
 // (|lo| < 2^-10 |x|) and is truncated to its own top 19 bits by the tensor core: 2^-21 relative overall.
@@ -104,7 +92,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <bool BULK>
 __global__ void __launch_bounds__(kTcThreads, 1)
 basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ ex, float* __restrict__ disp,
                 int nframes, int rows_pad, int ntiles, long long* __restrict__ trace, int store_policy) {
@@ -112,13 +99,11 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
   // optional per-role timeline of CTA 0 (diagnostics): trace[role * 64 + it * 4 + k] = clock64()
   const bool tracing = trace != nullptr && blockIdx.x == 0;
 #define VP_TRACE(role, it, k) do { if (tracing && (it) < 16) trace[(role) * 64 + (it) * 4 + (k)] = clock64(); } while (0)
-  constexpr int kStagesA = stages_a(BULK), kOffAlo = off_alo(BULK), kOffB = off_b(BULK);
   const int n_mma = (nframes + 15) & ~15;  // <= kTcN
   const int half_b = n_mma * 128;          // bytes of one K-half of a B tile
   uint8_t* smem_bhi = smem + kOffB;
   uint8_t* smem_blo = smem_bhi + 2 * half_b;
-  float* stage_tile = reinterpret_cast<float*>(smem_blo + 2 * half_b);  // BULK: [n_mma frames][128 rows]
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_blo + 2 * half_b + (BULK ? n_mma * 512 : 0));  // TMA landed
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_blo + 2 * half_b);  // TMA landed
   uint64_t* bar_afree = bar_full + kStagesA;                         // [3] MMAs that read the A stage completed
   uint64_t* bar_split = bar_afree + kStagesA;                        // [2] hi/lo tiles ready for the MMA
   uint64_t* bar_mma = bar_split + kStagesL;                          // [2] accumulator complete (and lo tile free)
@@ -249,36 +234,6 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
     const int quarter = warp & 3;        // TMEM lanes this warp may read: 32 * (warp % 4) ..
     const int group = ew >> 2;           // two warps per lane quarter alternate over 16-column chunks
     int it = 0;
-    if constexpr (BULK) {
-      // TMEM -> registers -> staging tile [frame][row] -> one 512-byte bulk store per frame, issued by lane 0 of
-      // every epilogue warp (frames ew, ew + 8, ...; bulk groups are per thread, so each issuer waits for its own)
-      for (int m = first; m < ntiles; m += step, ++it) {
-        const int sl = it & 1;
-        ptx::mbar_wait(bar_mma + sl, (it >> 1) & 1);
-        ptx::tc_fence_after();
-        if (lane == 0) ptx::bulk_wait_group_read0();        // this thread's stores of the previous tile have read the staging tile
-        ptx::named_barrier_sync(1, kEpiThreads);
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * kTcN);
-        float* col = stage_tile + quarter * 32 + lane;      // row of this lane inside the tile
-        for (int c0 = group * 16; c0 < n_mma; c0 += 32) {
-          uint32_t r[16];
-          ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) col[(c0 + j) * kTcM] = __uint_as_float(r[j]);   // 32 lanes: 128 contiguous bytes
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(bar_accfree + sl);                 // TMEM drained: the next MMA may reuse the accumulator
-        ptx::fence_proxy_async();                           // staging writes -> visible to the bulk copies
-        ptx::named_barrier_sync(1, kEpiThreads);
-        if (lane == 0) {
-          for (int c = ew; c < nframes; c += kEpiThreads / 32)
-            ptx::bulk_s2g(disp + (size_t)c * rows_pad + (size_t)m * kTcM, stage_tile + c * kTcM, kTcM * sizeof(float));
-          ptx::bulk_commit_group();
-        }
-      }
-      if (lane == 0) ptx::bulk_wait_group0();
-    } else
     for (int m = first; m < ntiles; m += step, ++it) {
       const int sl = it & 1;
       if (ew == 0 && lane == 0) VP_TRACE(3, it, 0);
@@ -306,6 +261,8 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
             if (c0 + j < nframes) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
         }
       }
+      // (loading all of a warp's chunks back to back, waiting once and releasing the accumulator before the stores
+      // was measured in round 2: 19.5 vs 18.4 us at 75 frames, equal at 96 / 128 -- no gain, not kept)
       ptx::tc_fence_before();
       ptx::mbar_arrive(bar_accfree + sl);
       if (ew == 0 && lane == 0) VP_TRACE(3, it, 2);
@@ -388,11 +345,7 @@ int basis_tc_prepare(vp_model* m) {
     return VP_ERR_CUDA;
   }
   std::memcpy(m->tmap_exb, &map, sizeof(map));
-  VP_CUDA(cudaFuncSetAttribute(basis_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcN, false)));
-  // the opt-in flavour must never take the default one down with it
-  g_bulk_ok = cudaFuncSetAttribute(basis_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem()) ==
-              cudaSuccess;
-  (void)cudaGetLastError();
+  VP_CUDA(cudaFuncSetAttribute(basis_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(kTcN)));
   m->have_tmap = true;
   return VP_OK;
 }
@@ -413,15 +366,9 @@ int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nfram
   for (int t0 = 0; t0 < nframes; t0 += kTcN) {
     const int n = std::min(kTcN, nframes - t0);
     const int n_mma = (n + 15) & ~15;
-    static const int bulk_env = [] { const char* e = std::getenv("VPB200_BASIS_EPI"); return e ? std::atoi(e) : 0; }();
-    if (bulk_env && g_bulk_ok && trace_dev == nullptr && tc_smem_bytes(n_mma, true) <= max_dyn_smem())
-      basis_tc_kernel<true><<<grid, kTcThreads, tc_smem_bytes(n_mma, true), st>>>(
-          map, ex_dev + (size_t)t0 * VP_N_EX, disp_dev + (size_t)t0 * m->rows_pad, n, m->rows_pad, ntiles, trace_dev,
-          store_policy);
-    else
-      basis_tc_kernel<false><<<grid, kTcThreads, tc_smem_bytes(n_mma, false), st>>>(
-          map, ex_dev + (size_t)t0 * VP_N_EX, disp_dev + (size_t)t0 * m->rows_pad, n, m->rows_pad, ntiles, trace_dev,
-          store_policy);
+    basis_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(n_mma), st>>>(
+        map, ex_dev + (size_t)t0 * VP_N_EX, disp_dev + (size_t)t0 * m->rows_pad, n, m->rows_pad, ntiles, trace_dev,
+        store_policy);
     VP_LAUNCH_CHECK();
   }
   return VP_OK;

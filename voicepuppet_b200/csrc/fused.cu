@@ -200,12 +200,17 @@ resolve_vcol_kernel(const unsigned long long* __restrict__ keys, EpochKey km, co
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t t = km.tri_mask - (static_cast<uint32_t>(k[i]) & km.tri_mask);  // winner's ORIGINAL index
-    t4[i] = (k[i] >= km.epoch_field) ? __ldg(tri_by_orig + t) : make_int4(-1, 0, 0, 0);
+    const bool same = i > 0 && k[i] == k[i - 1];   // same triangle as the pixel to the left: reuse its colour
+    t4[i] = same ? make_int4(-2, 0, 0, 0) : ((k[i] >= km.epoch_field) ? __ldg(tri_by_orig + t) : make_int4(-1, 0, 0, 0));
   }
   uint32_t col[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    col[i] = (t4[i].x >= 0) ? flat_color_packed(__ldg(vc + t4[i].x), __ldg(vc + t4[i].y), __ldg(vc + t4[i].z)) : 0u;
+  for (int i = 0; i < 4; ++i) {
+    if (t4[i].x == -2)
+      col[i] = col[i - 1];
+    else
+      col[i] = (t4[i].x >= 0) ? flat_color_packed(__ldg(vc + t4[i].x), __ldg(vc + t4[i].y), __ldg(vc + t4[i].z)) : 0u;
+  }
   // 12 bytes of RGB for 4 pixels as three 32-bit words
   const uint32_t w0 = (col[0] & 0xFFFFFFu) | ((col[1] & 0xFFu) << 24);
   const uint32_t w1 = ((col[1] >> 8) & 0xFFFFu) | ((col[2] & 0xFFFFu) << 16);
@@ -220,8 +225,11 @@ resolve_vcol_kernel(const unsigned long long* __restrict__ keys, EpochKey km, co
   }
 }
 
+// Measured on B200 (profiles/r02d_paths.txt): the separate kernels win at every BASELINE resolution (the fused
+// kernel runs its two phases back to back in the same warps at 20 warps/SM, the separate kernels overlap across
+// the two chunk streams), so the fused kernel is taken only on request (vp_set_raster_path(m, 2)).
 bool fused_available(const vp_model* m) {
-  return m->fused_ok && m->fused_mode == 0 && m->ntiles > 0 && m->vertex_mode == 0;
+  return m->fused_ok && m->fused_mode == 2 && m->ntiles > 0 && m->vertex_mode == 0;
 }
 
 int launch_fused(vp_model* m, const float* disp_dev, int nframes, const void* frame_constants, uint32_t* vcol,

@@ -120,7 +120,7 @@ struct vp_model {
   int* halo = nullptr;
   uint16_t* ring = nullptr;     // [nver][8] local triangle index per point_buf slot
   uint32_t* fan = nullptr;      // [nver][5] fan records (tiles with TileDesc::fan)
-  // optional bank-conflict-aware slot tables (VPB200_VERTEX_SLOTS=1 at model creation; see Topology)
+  // bank-conflict-aware slot tables of the fan kernel (see Topology)
   int* slot_off = nullptr;
   uint16_t* slot_tab = nullptr;
   uint32_t* fan_slot = nullptr;
@@ -130,7 +130,7 @@ struct vp_model {
   uint32_t* own_ltri = nullptr;
   int4* tri_by_orig = nullptr;  // [ntri] internal vertex ids of ORIGINAL triangle t
   bool fused_ok = false;
-  int fused_mode = 0;           // 0 = fused kernel when the mesh allows it, 1 = separate vertex / scatter / resolve kernels
+  int fused_mode = 0;           // vp_set_raster_path: 0 = automatic (separate kernels), 1 = separate, 2 = fused kernel
   int* tile_list = nullptr;     // tile ids: the n_fan_tiles fan tiles first, then the generic ones
   int n_fan_tiles = 0;
   // TMA descriptor of exb for the tcgen05 basis kernel (a CUtensorMap, kept opaque here)
@@ -153,11 +153,17 @@ struct vp_model {
   // the two halves of the chunk workspaces), so the ramp-up of one chunk's kernels fills the tails of the other's
   cudaStream_t aux_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_basis = nullptr, ev_aux_done = nullptr, ev_main_done = nullptr;
+  // recorded on the caller's stream at the end of every asynchronous render; the entry points that rewrite model
+  // state (identity, base shape, texture, workspaces) on another stream wait for it first (wait_for_renders)
+  cudaEvent_t ev_render_done = nullptr;
+  bool render_pending = false;
+  cudaStream_t last_render_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_render[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
 
   int basis_mode = 0;           // vp::BasisMode
-  int vertex_mode = 0;          // 0 = fan records where available, 1 = generic kernel everywhere
+  int vertex_mode = 0;          // 0 = fan records where available (bank-aware slots), 1 = generic kernel everywhere,
+                                // 2 = fan records with local vertex i staged at slot i (tests compare the placements)
   // profiling
   bool profiling = false;
   float prof_ms[8] = {0};
@@ -167,6 +173,29 @@ struct vp_model {
 };
 
 namespace vp {
+
+// Call (under m->mu) before touching state an asynchronous render still in flight may read: the renders are
+// ordered on their caller's stream, which need not be the stream (often the legacy one) the setters use.
+inline int wait_for_renders(vp_model* m) {
+  if (m->render_pending && m->ev_render_done) {
+    VP_CUDA(cudaEventSynchronize(m->ev_render_done));
+    m->render_pending = false;
+  }
+  return VP_OK;
+}
+
+// A render on `st` reuses the workspaces of the previous one: order it behind that one when it ran on another stream.
+inline int order_after_renders(vp_model* m, cudaStream_t st) {
+  if (m->render_pending && m->ev_render_done && m->last_render_stream != st)
+    VP_CUDA(cudaStreamWaitEvent(st, m->ev_render_done, 0));
+  return VP_OK;
+}
+inline void note_render(vp_model* m, cudaStream_t st) {
+  if (m->ev_render_done && cudaEventRecord(m->ev_render_done, st) == cudaSuccess) {
+    m->render_pending = true;
+    m->last_render_stream = st;
+  }
+}
 
 enum ProfSlot { kProfBasis = 0, kProfVertex = 1, kProfScatter = 2, kProfResolve = 3, kProfFused = 4, kProfSlots = 5 };
 

@@ -87,7 +87,7 @@ void free_model(vp_model* m) {
   }
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->ev_stage) cudaEventDestroy(m->ev_stage);
-  for (cudaEvent_t e : {m->ev_fork, m->ev_basis, m->ev_aux_done, m->ev_main_done})
+  for (cudaEvent_t e : {m->ev_fork, m->ev_basis, m->ev_aux_done, m->ev_main_done, m->ev_render_done})
     if (e) cudaEventDestroy(e);
   if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
   if (m->h_stage) cudaFreeHost(m->h_stage);
@@ -110,9 +110,9 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
 
   std::vector<double> xyz((size_t)m->rows);
   for (size_t i = 0; i < xyz.size(); ++i) xyz[i] = load_as_double(meanshape, ms64, i);
-  // VPB200_VERTEX_SLOTS=1: also build the bank-conflict-aware slot tables (opt-in until measured on the GPU)
-  const char* slots_env = std::getenv("VPB200_VERTEX_SLOTS");
-  const bool with_slots = slots_env && std::atoi(slots_env) != 0;
+  // bank-conflict-aware shared-memory slots of the fan vertex kernel: measured on B200 (profiles/r02a_optin_flavours.jsonl:
+  // 56.3 -> 51.8 us per 75 frames at 256x256), always built
+  const bool with_slots = true;
   VP_TRY(build_topology(m->topo, nver, ntri, tri, point_buf, xyz.data(), with_slots));
   const std::vector<int>& i2o = m->topo.v_int2orig;
 
@@ -207,7 +207,7 @@ int create_model(vp_model* m, int nver, int ntri, const void* meanshape, const v
   VP_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
   VP_CUDA(cudaEventCreateWithFlags(&m->ev_stage, cudaEventDisableTiming));
   VP_CUDA(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&m->ev_fork, &m->ev_basis, &m->ev_aux_done, &m->ev_main_done})
+  for (cudaEvent_t* e : {&m->ev_fork, &m->ev_basis, &m->ev_aux_done, &m->ev_main_done, &m->ev_render_done})
     VP_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     VP_CUDA(cudaEventCreateWithFlags(&m->ev_render[i], cudaEventDisableTiming));
@@ -256,7 +256,8 @@ extern "C" int vp_set_basis_mode(vp_model* m, int mode) {
 
 extern "C" int vp_set_raster_path(vp_model* m, int mode) {
   VP_REQUIRE(m != nullptr, "null model");
-  VP_REQUIRE(mode == 0 || mode == 1, "raster path must be 0 (fused when available) or 1 (separate kernels)");
+  VP_REQUIRE(mode == 0 || mode == 1 || mode == 2, "raster path must be 0 (automatic), 1 (separate kernels) or 2 (fused kernel)");
+  VP_REQUIRE(mode != 2 || m->fused_ok, "the fused kernel cannot take this mesh (vp_model_fused_available() == 0)");
   std::lock_guard<std::mutex> lock(m->mu);
   m->fused_mode = mode;
   return VP_OK;
@@ -266,7 +267,7 @@ extern "C" int vp_model_fused_available(const vp_model* m) { return (m && m->fus
 
 extern "C" int vp_set_vertex_mode(vp_model* m, int mode) {
   VP_REQUIRE(m != nullptr, "null model");
-  VP_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (auto) or 1 (generic kernel)");
+  VP_REQUIRE(mode == 0 || mode == 1 || mode == 2, "mode must be 0 (auto), 1 (generic kernel) or 2 (fan records, identity slots)");
   std::lock_guard<std::mutex> lock(m->mu);
   m->vertex_mode = mode;
   return VP_OK;
@@ -278,6 +279,7 @@ extern "C" int vp_set_identity(vp_model* m, const float* id_coeff80, const float
   VP_REQUIRE(m != nullptr, "null model");
   std::lock_guard<std::mutex> lock(m->mu);
   VP_CUDA(cudaSetDevice(m->device));
+  VP_TRY(wait_for_renders(m));
   cudaStream_t st = nullptr;
   if (id_coeff80)
     VP_CUDA(cudaMemcpyAsync(m->coeff_tmp, id_coeff80, VP_N_ID * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -294,6 +296,7 @@ extern "C" int vp_set_base_shape(vp_model* m, const double* shape) {
   VP_REQUIRE(m != nullptr && shape != nullptr, "null argument");
   std::lock_guard<std::mutex> lock(m->mu);
   VP_CUDA(cudaSetDevice(m->device));
+  VP_TRY(wait_for_renders(m));
   std::vector<double> tmp((size_t)m->rows);
   const std::vector<int>& i2o = m->topo.v_int2orig;
   for (size_t i = 0; i < i2o.size(); ++i)
@@ -307,6 +310,7 @@ extern "C" int vp_set_texture(vp_model* m, const float* texture) {
   VP_REQUIRE(m != nullptr && texture != nullptr, "null argument");
   std::lock_guard<std::mutex> lock(m->mu);
   VP_CUDA(cudaSetDevice(m->device));
+  VP_TRY(wait_for_renders(m));
   std::vector<float> tmp((size_t)m->rows);
   const std::vector<int>& i2o = m->topo.v_int2orig;
   for (size_t i = 0; i < i2o.size(); ++i)
@@ -321,6 +325,7 @@ extern "C" int vp_get_texture(vp_model* m, float* texture) {
   std::lock_guard<std::mutex> lock(m->mu);
   VP_REQUIRE(m->have_tex, "no texture set (call vp_set_identity first)");
   VP_CUDA(cudaSetDevice(m->device));
+  VP_TRY(wait_for_renders(m));
   std::vector<float> tmp((size_t)m->rows);
   VP_CUDA(cudaMemcpy(tmp.data(), m->tex, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
   const std::vector<int>& i2o = m->topo.v_int2orig;
@@ -334,6 +339,7 @@ extern "C" int vp_get_base_shape(vp_model* m, double* shape) {
   std::lock_guard<std::mutex> lock(m->mu);
   VP_REQUIRE(m->have_base, "no base shape set (call vp_set_identity first)");
   VP_CUDA(cudaSetDevice(m->device));
+  VP_TRY(wait_for_renders(m));
   std::vector<double> tmp((size_t)m->rows);
   VP_CUDA(cudaMemcpy(tmp.data(), m->base, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
   const std::vector<int>& i2o = m->topo.v_int2orig;

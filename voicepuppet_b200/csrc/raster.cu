@@ -64,7 +64,7 @@ EpochKey make_epoch_key(int ntri, uint32_t epoch) {
 
 // Boxes up to this many pixels are walked by their own lane; larger ones are flattened over the warp (raster_walk.cuh).
 int inline_box_pixels() {
-  static const int v = [] { const char* e = std::getenv("VPB200_INLINE_BOX"); return e ? std::atoi(e) : 12; }();
+  static const int v = [] { const char* e = std::getenv("VPB200_INLINE_BOX"); return e ? std::atoi(e) : 64; }();
   return v;
 }
 
@@ -120,6 +120,14 @@ int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_co
   return VP_OK;
 }
 
+// Host-pointer entry points: a triangle index outside the vertex buffer would make the kernels read out of bounds
+// (the reference's C++ has no check either and reads whatever is there: mesh_core.cpp:186-188).
+static int check_triangle_indices(const int* triangles, int ntri, int nver) {
+  for (size_t i = 0; i < (size_t)ntri * 3; ++i)
+    VP_REQUIRE(triangles[i] >= 0 && triangles[i] < nver, "triangle index outside the vertex buffer");
+  return VP_OK;
+}
+
 static int check_raster_args(int nver, int ntri, int h, int w) {
   VP_REQUIRE(nver >= 0 && ntri >= 0, "negative element count");
   VP_REQUIRE(h > 0 && w > 0 && h <= 16384 && w <= 16384, "image size must be in 1..16384");
@@ -169,6 +177,7 @@ extern "C" int vp_render_colors_core(unsigned char* image, unsigned char* face_m
   VP_REQUIRE(c >= 1, "c >= 1");
   VP_REQUIRE(image && face_mask && depth_buffer, "null output buffer");
   VP_REQUIRE(ntri == 0 || (vertices && triangles && colors), "null mesh buffer");
+  VP_TRY(check_triangle_indices(triangles, ntri, nver));
   int device = 0;
   VP_CUDA(cudaGetDevice(&device));
   std::lock_guard<std::mutex> lock(g_scratch_mutex);
@@ -208,6 +217,7 @@ extern "C" int vp_rasterize_triangles_core(const float* vertices, const int* tri
   VP_TRY(check_raster_args(nver, ntri, h, w));
   VP_REQUIRE(depth_buffer && triangle_buffer && barycentric_weight, "null output buffer");
   VP_REQUIRE(ntri == 0 || (vertices && triangles), "null mesh buffer");
+  VP_TRY(check_triangle_indices(triangles, ntri, nver));
   int device = 0;
   VP_CUDA(cudaGetDevice(&device));
   std::lock_guard<std::mutex> lock(g_scratch_mutex);

@@ -340,7 +340,12 @@ resolve_packed_kernel(const unsigned long long* __restrict__ keys, EpochKey km,
   for (int i = 0; i < 4; ++i) {
     const bool live = k[i] >= km.epoch_field;  // written during this chunk
     const uint32_t t = km.tri_mask - (static_cast<uint32_t>(k[i]) & km.tri_mask);  // winner's ORIGINAL index
-    col[i] = live ? __ldg(tc + __ldg(t_orig2int + t)) : 0u;
+    // neighbouring pixels of one triangle carry the same key (flat depth): one gather chain serves them all
+    // (at 1024x1024 a triangle covers ~8 pixels, so this removes about half of the dependent gathers)
+    if (i > 0 && k[i] == k[i - 1])
+      col[i] = col[i - 1];
+    else
+      col[i] = live ? __ldg(tc + __ldg(t_orig2int + t)) : 0u;
   }
   // 12 bytes of RGB for 4 pixels as three 32-bit words
   const uint32_t w0 = (col[0] & 0xFFFFFFu) | ((col[1] & 0xFFu) << 24);

@@ -22,6 +22,8 @@ constexpr unsigned kFullWarp = 0xFFFFFFFFu;
 
 // s: bounding box + edge set-up (valid when n > 0); key: the triangle's z-buffer key; n: box pixels (0 = nothing to
 // do); rec: this warp's staging, float4[4][32]; keys: the frame's z-buffer.  All 32 lanes must call.
+// (Testing two adjacent pixels per iteration of the lane's own loop -- 52 instead of 2 x 38 instructions -- was
+// measured in round 2 and changed nothing at 512x512 / 1024x1024, profiles/r02f_pairs_chunks.txt: not kept.)
 __device__ __forceinline__ void walk_boxes(const TriSetup& s, unsigned long long key, int n, int inline_max,
                                            float4 (*rec)[32], unsigned long long* __restrict__ keys, int w,
                                            unsigned lane) {

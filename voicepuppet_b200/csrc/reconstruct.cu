@@ -357,7 +357,8 @@ __device__ __forceinline__ void finish_vertex(const VertexArgs& a, const FrameSh
 // and the block synchronises once.  Shared memory holds positions only (no per-triangle pass).
 // SLOTS: local vertex i is staged at shared-memory slot slot_tab[i] instead of i and the fan records come in slot
 // space (fan_slot), which roughly halves the bank conflicts of the gathers in the quarter-warp model
-// (tools/bank_conflict_sim.py); opt-in (VPB200_VERTEX_SLOTS=1 at model creation), not yet measured on the GPU.
+// (tools/bank_conflict_sim.py); measured on B200: 56.3 -> 51.8 us per 75 frames at 256x256, so it is the default
+// (vp_set_vertex_mode(m, 2) selects the identity placement, for the tests).
 template <int MIN_BLOCKS, bool FAST, bool SLOTS = false>
 __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) vertex_fan_kernel(const VertexArgs a) {
   using Frame = typename std::conditional<FAST, FrameFast, FrameShared>::type;
@@ -600,7 +601,7 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
     dim3 grid(n_fan, (nframes + a.frames_per_block - 1) / a.frames_per_block);
     static const int slow_env = [] { const char* e = std::getenv("VPB200_VERTEX_SLOW"); return e ? std::atoi(e) : 0; }();
     const bool fast = !a.has_out && a.vrec != nullptr && !slow_env;  // raster records only: the folded constants
-    if (fast && m->have_slots) {
+    if (fast && m->have_slots && m->vertex_mode != 2) {
       vertex_fan_kernel<8, true, true><<<grid, kTileV, 0, st>>>(a);
     } else if (fast) {
       if (minb <= 6)
@@ -731,6 +732,7 @@ extern "C" int vp_reconstruct(vp_model* m, const vp_frames* fr, const vp_recon_o
   VP_REQUIRE(m->have_base, "no base shape (call vp_set_identity or vp_set_base_shape first)");
   VP_REQUIRE(!out->face_color || m->have_tex, "face_color requested but no texture set");
   VP_CUDA(cudaSetDevice(m->device));
+  VP_TRY(wait_for_renders(m));   // shares ws_params / ws_disp / ws_fshared with renders that may still be in flight
   cudaStream_t st = nullptr;
   const int T = fr->nframes;
   const int chunk = 64;

@@ -24,14 +24,16 @@ size_t env_size(const char* name, size_t dflt) {
 // Frames per raster chunk.  Measured on B200 (profiles/r01_chunk_sweep.txt): large launches beat
 // L2 residency of the intermediates -- one 75-frame chunk at 256x256 (134 MB of intermediates) runs 10 %
 // faster than two 38-frame chunks -- so the device-output path takes the largest chunk within
-// VPB200_CHUNK_MB (default 192 MB of vertex records + z-buffer keys + per-triangle colours).  The
+// VPB200_CHUNK_MB (default 320 MB of vertex records + z-buffer keys + per-triangle colours; the round-2 sweep at
+// 512x512 and 1024x1024, profiles/r02f_pairs_chunks.txt, confirms it: chunks small enough to keep the z-buffer
+// keys in the 126 MB L2 lose more on launch efficiency than they save on HBM traffic).  The
 // host-output path cuts the sequence into at least four chunks so that the device->host drain of one
 // chunk overlaps the rendering of the next.  Chunks are equal-sized so that no launch runs nearly empty.
 int chunk_frames(const vp_model* m, int res, int nframes, bool host_outputs) {
   const size_t per_frame = fused_available(m) ? (size_t)m->vrec_stride * 4 + (size_t)res * res * 8
                                               : (size_t)m->vrec_stride * 16 + (size_t)res * res * 8 + (size_t)m->ntri * 4;
   const size_t forced = env_size("VPB200_CHUNK_FRAMES", 0);
-  size_t c = forced ? forced : (env_size("VPB200_CHUNK_MB", 192) << 20) / per_frame;
+  size_t c = forced ? forced : (env_size("VPB200_CHUNK_MB", 320) << 20) / per_frame;
   c = std::max<size_t>(c, 4);
   c = std::min<size_t>(c, 1024);
   const size_t t = (size_t)std::max(nframes, 1);
@@ -113,6 +115,7 @@ struct ChunkRunner {
 
   int init(int nframes_, int res_, int chunk_cap_, int nchunks, const float* ex, const FrameParams* params,
            int rotate_first_, bool allow_dual = true) {
+    VP_TRY(order_after_renders(m, st));
     nframes = nframes_;
     res = res_;
     chunk_cap = chunk_cap_;
@@ -224,6 +227,7 @@ struct ChunkRunner {
       }
     }
     if (rc != VP_OK) m->key_epoch = 0;
+    note_render(m, st);
     prof.finish();
     return rc;
   }
@@ -344,6 +348,7 @@ extern "C" int vp_render_sequence(vp_model* m, const vp_frames* fr, int res, uns
   VP_REQUIRE(m->have_base && m->have_tex, "no identity set (call vp_set_identity first)");
   VP_CUDA(cudaSetDevice(m->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VP_TRY(order_after_renders(m, st));   // the uploads below rewrite workspaces a render on another stream may still read
 
   // per-frame inputs: one upload for the whole sequence (T * 448 bytes) out of page-locked staging, so
   // that the copies are asynchronous; the staging is reused only after the previous call's uploads ran

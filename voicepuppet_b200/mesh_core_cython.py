@@ -37,8 +37,7 @@ def _need(name, a, count):
     raise ValueError("buffer '%s' holds %d elements, the call needs %d" % (name, a.size, count))
 
 
-def render_colors_core(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c):
-  """mesh_core_cython.pyx:64-78 -> mesh_core.cpp:169-231 (flat depth, flat colour)."""
+def _render_colors(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c, triangle_id):
   image = _buffer('image', image, np.uint8, 1)
   face_mask = _buffer('face_mask', face_mask, np.uint8, 1)
   vertices = _buffer('vertices', vertices, np.float32, 1)
@@ -57,18 +56,21 @@ def render_colors_core(image, face_mask, vertices, triangles, colors, depth_buff
     if t.min() < 0 or t.max() >= nver:
       raise ValueError('triangle index outside the vertex buffer (the reference would read out of bounds)')
   _lib.check(_lib.lib().vp_render_colors_core(_lib.ptr(image), _lib.ptr(face_mask), _lib.ptr(vertices),
-                                              _lib.ptr(triangles), _lib.ptr(colors), _lib.ptr(depth_buffer), None,
+                                              _lib.ptr(triangles), _lib.ptr(colors), _lib.ptr(depth_buffer),
+                                              None if triangle_id is None else _lib.ptr(triangle_id),
                                               nver, ntri, h, w, c))
+
+
+def render_colors_core(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c):
+  """mesh_core_cython.pyx:64-78 -> mesh_core.cpp:169-231 (flat depth, flat colour)."""
+  _render_colors(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c, None)
 
 
 def render_colors_with_triangle_id(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c):
   """render_colors_core that also returns the winning triangle per pixel (-1 = untouched), which
-  the reference computes implicitly but never stores."""
+  the reference computes implicitly but never stores.  Same argument checks as render_colors_core."""
   triangle_id = np.empty(int(h) * int(w), dtype=np.int32)
-  nver = vertices.size // 3
-  _lib.check(_lib.lib().vp_render_colors_core(_lib.ptr(image), _lib.ptr(face_mask), _lib.ptr(vertices),
-                                              _lib.ptr(triangles), _lib.ptr(colors), _lib.ptr(depth_buffer),
-                                              _lib.ptr(triangle_id), nver, int(ntri), int(h), int(w), int(c)))
+  _render_colors(image, face_mask, vertices, triangles, colors, depth_buffer, ntri, h, w, c, triangle_id)
   return triangle_id
 
 

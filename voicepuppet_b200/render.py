@@ -160,6 +160,26 @@ def push_plan(n_local, world):
       return plan
   if n_local < 48:
     return [n_local]
+  if n_local >= 256:
+    # long shards (the 12000-frame configuration: 1500 frames per GPU at 8): chunks the size of a basis group (96
+    # frames, so no chunk straddles two contractions), every one pushed under the rendering of the next; the first
+    # group is cut 32 + 64 so that the first push starts early, the last one ends with a 32-frame chunk so that the
+    # push left exposed at the end is short
+    group = int(os.environ.get('VPB200_BASIS_FRAMES', '96'))
+    n_groups = -(-n_local // group)
+    per = -(-n_local // n_groups)
+    per = -(-per // 1) if per <= group else group
+    plan, left = [], n_local
+    while left > 0:
+      g = min(per, left)
+      if not plan and g > 48:
+        plan += [32, g - 32]
+      elif left == g and g > 64:
+        plan += [g - 32, 32]
+      else:
+        plan.append(g)
+      left -= g
+    return plan
   edge = max(8, n_local // 8)
   mid = n_local - 2 * edge
   n_mid = max(2, -(-mid // 96))     # measured at 4 and 8 GPUs: two middle chunks beat one (profiles/r01_multigpu.txt)
@@ -254,6 +274,14 @@ class PeerFrameBuffer(object):
     self.flags_ptr = start + ((n_bytes + 127) // 128) * 128
     if world > 32:
       raise ValueError('PeerFrameBuffer supports up to 32 ranks')
+    dist.barrier(group)          # every rank has mapped the buffer before anybody renders, signals or waits
+
+  def check(self):
+    """After synchronising: raise if a completion wait on this device gave up (a rank never signalled)."""
+    from . import _lib
+    n = _lib.lib().vp_peer_timeouts()
+    if n != 0:
+      raise _lib.VpError('peer gather: %d completion wait(s) timed out (VPB200_PEER_TIMEOUT_S); frames are incomplete' % n)
 
   def render_into(self, dm, ex_dev, params_dev, rotate_first, mode='auto', notify_frames=None):
     """Render this rank's frames and land them in its slice of rank 0's buffer, then publish a
@@ -365,6 +393,7 @@ def render_sequence_sharded(coeffs, facemodel, res=IMG, angles='jitter', group=N
       full = buf.render_into(dm, ex_dev, params_dev, rotate_first, mode='store' if gather == 'p2p-store' else ('push' if gather == 'p2p-push' else 'auto'),
                              notify_frames=notify_frames)
       torch.cuda.current_stream(device).synchronize()
+      buf.check()
       dist.barrier(group)          # nobody unmaps before every rank's stores are complete
       buf.close()
     else:

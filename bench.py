@@ -605,6 +605,13 @@ def run_sharded(env, name, steps, warmup):
     return None, peer
   _, total_bytes = algorithmic_bytes(frames, res)
   peak, _ = measured_peaks()
+  eff_mode = peer.effective_mode(peer_mode, end - begin) if peer is not None else 'nccl'
+  gather_label = {
+      'push': 'finished chunks of frames pushed into rank 0 buffer over NVLink (CUDA IPC peer memory, copy engine) under '
+              'the rendering of the next chunk (plan %s); device-side completion flags' % render.push_plan(end - begin, world),
+      'store': 'resolve kernels store straight into rank 0 buffer over NVLink (CUDA IPC peer memory); device-side completion flags',
+      'store-chunks': 'resolve kernels store straight into rank 0 buffer over NVLink, chunked over two streams',
+      'nccl': 'NCCL gather of uint8 frames to rank 0, per chunk on a side stream'}.get(eff_mode, eff_mode)
   frame_bytes = res * res * 3
   ingest = (world - 1) * per * frame_bytes
   exposed_ms = max(0.0, ms_per_step - render_ms)
@@ -612,9 +619,7 @@ def run_sharded(env, name, steps, warmup):
   return {
       'name': name, 'frames': frames, 'res': res, 'ms_per_step': ms_per_step, 'value': frames / (ms_per_step * 1e-3),
       'launches': int(launches), 'clocks': clocks, 'gather_verified': verified,
-      'gather': {'mode': ('finished chunks of frames pushed into rank 0 buffer over NVLink (CUDA IPC peer memory, copy engine) '
-                          'under the rendering of the next chunk; device-side completion flags' if peer is not None
-                          else 'NCCL gather of uint8 frames to rank 0, per chunk on a side stream'),
+      'gather': {'mode': gather_label,
                  'rank0_ingest_bytes_per_step': ingest, 'render_only_ms': render_ms, 'exposed_gather_ms': exposed_ms,
                  'rank0_ingest_gbs_over_step': round(ingest / ms_per_step / 1e6, 1),
                  'completion_wait_timeouts': int(lib.vp_peer_timeouts())},

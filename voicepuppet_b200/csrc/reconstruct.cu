@@ -4,6 +4,8 @@
 // Reference: utils/reconstruct_mesh.py:20-29 (Shape_formation), :58-62 (Texture_formation),
 // :35-52 (Compute_norm), :100-120 (Projection_layer), :129-168 (Illumination_layer),
 // :172-223 (Reconstruction / Reconstruction_rotation).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -154,9 +156,86 @@ basis_simt_kernel(const float* __restrict__ exb, const float* __restrict__ ex, f
   }
 }
 
+// Same contraction, the basis tile landed by TWO TMA tensor loads per CTA (the 2-D descriptor of the tcgen05 kernel:
+// box = 32 floats x 128 rows, 128-byte swizzle) instead of 128 bulk copies of 256 bytes: the per-SM TMA unit was the
+// limiter of the GEMV-sized launches (ncu round 2: 17.6 us for ONE frame = 1.5 TB/s, every CTA queueing 128 tiny
+// copies).  The swizzle also makes the row-per-thread reads conflict free without padding: 16-byte chunk c of row r
+// of a K half sits at (r / 8) * 1024 + (r % 8) * 128 + ((c ^ (r % 8)) * 16), so the 8 lanes of a quarter-warp hit 8
+// different bank groups.
+__global__ void __launch_bounds__(kBasisRows)
+basis_simt_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restrict__ ex, float* __restrict__ disp,
+                      int nframes, int rows_pad) {
+  __shared__ __align__(1024) uint8_t a_s[kBasisRows * VP_N_EX * sizeof(float)];  // two K halves of 16 KB
+  __shared__ __align__(16) float ex_s[kBasisFrames * VP_N_EX];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int row = blockIdx.x * kBasisRows + tid;
+  constexpr int kHalf = kBasisRows * 32 * sizeof(float);
+  if (tid == 0) {
+    ptx::mbar_init(&bar, 1);
+    ptx::fence_mbar_init();
+    ptx::mbar_arrive_expect_tx(&bar, 2 * kHalf);
+    ptx::tma_load_2d(a_s, &tmap_a, 0, blockIdx.x * kBasisRows, &bar);
+    ptx::tma_load_2d(a_s + kHalf, &tmap_a, 32, blockIdx.x * kBasisRows, &bar);
+  }
+  __syncthreads();
+  ptx::mbar_wait(&bar, 0);
+
+  float a[VP_N_EX];
+  {
+    const uint8_t* base = a_s + (tid >> 3) * 1024 + (tid & 7) * 128;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(base + h * kHalf + ((c ^ (tid & 7)) << 4));
+        a[32 * h + 4 * c + 0] = v.x;
+        a[32 * h + 4 * c + 1] = v.y;
+        a[32 * h + 4 * c + 2] = v.z;
+        a[32 * h + 4 * c + 3] = v.w;
+      }
+  }
+
+  for (int t0 = 0; t0 < nframes; t0 += kBasisFrames) {
+    const int nt = min(kBasisFrames, nframes - t0);
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(ex + (size_t)t0 * VP_N_EX);
+      float4* dst = reinterpret_cast<float4*>(ex_s);
+      for (int i = tid; i < kBasisFrames * VP_N_EX / 4; i += kBasisRows)
+        dst[i] = (i < nt * (VP_N_EX / 4)) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int t = 0; t < nt; t += 4) {  // 4 frames in flight per thread (ex_s is zero padded)
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < VP_N_EX / 4; ++j) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 e = *reinterpret_cast<const float4*>(ex_s + (t + u) * VP_N_EX + 4 * j);
+          acc[u] = fmaf(a[4 * j + 0], e.x, acc[u]);
+          acc[u] = fmaf(a[4 * j + 1], e.y, acc[u]);
+          acc[u] = fmaf(a[4 * j + 2], e.z, acc[u]);
+          acc[u] = fmaf(a[4 * j + 3], e.w, acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (t + u < nt) disp[(size_t)(t0 + t + u) * rows_pad + row] = acc[u];
+    }
+  }
+}
+
 int launch_basis_simt(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st) {
   if (nframes == 0) return VP_OK;
-  basis_simt_kernel<<<m->rows_pad / kBasisRows, kBasisRows, 0, st>>>(m->exb, ex_dev, disp_dev, nframes, m->rows_pad);
+  if (m->have_tmap) {
+    CUtensorMap map;
+    static_assert(sizeof(map) == sizeof(m->tmap_exb), "tensor map storage size");
+    std::memcpy(&map, m->tmap_exb, sizeof(map));
+    basis_simt_tma_kernel<<<m->rows_pad / kBasisRows, kBasisRows, 0, st>>>(map, ex_dev, disp_dev, nframes, m->rows_pad);
+  } else {  // no TMA descriptor (driver without cuTensorMapEncodeTiled): per-row bulk copies
+    basis_simt_kernel<<<m->rows_pad / kBasisRows, kBasisRows, 0, st>>>(m->exb, ex_dev, disp_dev, nframes, m->rows_pad);
+  }
   VP_LAUNCH_CHECK();
   return VP_OK;
 }

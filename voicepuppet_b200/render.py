@@ -160,25 +160,19 @@ def push_plan(n_local, world):
       return plan
   if n_local < 48:
     return [n_local]
-  if n_local >= 256:
-    # long shards (the 12000-frame configuration: 1500 frames per GPU at 8): chunks the size of a basis group (96
-    # frames, so no chunk straddles two contractions), every one pushed under the rendering of the next; the first
-    # group is cut 32 + 64 so that the first push starts early, the last one ends with a 32-frame chunk so that the
-    # push left exposed at the end is short
-    group = int(os.environ.get('VPB200_BASIS_FRAMES', '96'))
-    n_groups = -(-n_local // group)
-    per = -(-n_local // n_groups)
-    per = -(-per // 1) if per <= group else group
-    plan, left = [], n_local
-    while left > 0:
-      g = min(per, left)
-      if not plan and g > 48:
-        plan += [32, g - 32]
-      elif left == g and g > 64:
-        plan += [g - 32, 32]
-      else:
-        plan.append(g)
-      left -= g
+  if n_local >= 512:
+    # long shards (the 12000-frame configuration: 1500 frames per GPU at 8).  Measured at 2 GPUs
+    # (profiles/r02g_multi_n2_*.json): chunks of one basis group (94 frames) cost 8 % against the unchunked
+    # rendering, because every chunk is three launches with a ramp and a tail; so the chunks are 256 frames (the
+    # contraction runs 128 frames per launch inside a chunk), the first one cut 64 + 192 so that the first push
+    # starts early, the last one ending with a 64-frame chunk so that the push left exposed at the end is short.
+    chunk = int(os.environ.get('VPB200_PUSH_CHUNK', '256'))
+    n_full, rem = divmod(n_local, chunk)
+    plan = [64, chunk - 64] + [chunk] * (n_full - 1)
+    if rem > 96:
+      plan += [rem - 64, 64]
+    elif rem > 0:
+      plan += [rem]
     return plan
   edge = max(8, n_local // 8)
   mid = n_local - 2 * edge
@@ -283,6 +277,12 @@ class PeerFrameBuffer(object):
     if n != 0:
       raise _lib.VpError('peer gather: %d completion wait(s) timed out (VPB200_PEER_TIMEOUT_S); frames are incomplete' % n)
 
+  def effective_mode(self, mode, n_frames):
+    """What mode='auto' resolves to for a shard of n_frames frames."""
+    if mode != 'auto':
+      return mode
+    return 'store' if (self.world <= 2 and n_frames < 256) else 'push'
+
   def render_into(self, dm, ex_dev, params_dev, rotate_first, mode='auto', notify_frames=None):
     """Render this rank's frames and land them in its slice of rank 0's buffer, then publish a
     completion flag; on rank 0 the current stream then waits (on the device) until every rank's flag
@@ -291,15 +291,15 @@ class PeerFrameBuffer(object):
                      rank 0 by the copy engine on a side stream while the SMs render the next chunk
       mode='store' : the resolve kernel stores straight into the peer-mapped slice (no staging, no
                      copy; the kernel then runs at NVLink ingest speed)
-      mode='auto'  : 'store' for two ranks, 'push' beyond (measured on B200: 231 vs 261 us per 75-frame
-                     step at 2 GPUs, 303 vs 272 us at 4; profiles/r01_multigpu.txt)
+      mode='auto'  : 'store' for two ranks with short shards, 'push' otherwise (measured on B200: 231 vs 261 us per
+                     75-frame step at 2 GPUs, 303 vs 272 us at 4, profiles/r01_multigpu.txt; 6000-frame shards at
+                     2 GPUs: push 10.98 ms, store 13.3 ms per step, profiles/r02g_multi_n2_*.json)
     Returns the full buffer on rank 0, None elsewhere."""
     import ctypes
     import torch
     from . import _lib
     lib = _lib.lib()
-    if mode == 'auto':
-      mode = 'store' if self.world <= 2 else 'push'
+    mode = self.effective_mode(mode, ex_dev.shape[0])
     self.step += 1
     n = ex_dev.shape[0]
     compute = torch.cuda.current_stream(self.device)

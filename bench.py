@@ -465,14 +465,41 @@ def run_sharded(env, name, steps, warmup):
   world, rank, dev, dm, lib = env.world, env.rank, env.dev, env.dm, env.lib
   coeffs_all = synthetic.make_coeffs(frames, seed=1)
   angles_all = render.jitter_angle_sequence(frames)
-  begin, end = render.shard_bounds(frames, world, rank)
-  per = -(-frames // world)
-  coeffs, angles = coeffs_all[begin:end], angles_all[begin:end]
   dm.set_identity(coeffs_all[0:1, :80], coeffs_all[0:1, 144:224])
-  ex_dev, params_dev = render.device_inputs(coeffs, angles, dev)
   gather_mode = os.environ.get('VPB200_GATHER', 'p2p')
   peer_mode = os.environ.get('VPB200_PEER_MODE', 'auto')
-  peer = render.PeerFrameBuffer(per, res, world, rank, dev) if gather_mode == 'p2p' else None
+  # Root-aware sharding (peer-memory gather only): rank 0 also receives everybody else's frames through one NVLink
+  # port, which bounds the step from 8 ranks on; it renders a few more frames itself so that fewer cross the link.
+  # R = frames/s of one GPU, measured here on rank 0; B = rank 0's ingest, measured in round 2 (profiles/r02h_*).
+  root_frames, shard_model = None, None
+  if gather_mode == 'p2p' and world >= 3 and os.environ.get('VPB200_ROOT_AWARE', '1') == '1':
+    box = [None]
+    if rank == 0:
+      k = min(frames, 768)
+      ex_p, par_p = render.device_inputs(coeffs_all[:k], angles_all[:k], dev)
+      buf_p = torch.empty((k, res, res, 3), dtype=torch.uint8, device=dev)
+      best = None
+      for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        render.render_device(dm, ex_p, par_p, True, res, buf_p)
+        b.record()
+        torch.cuda.synchronize(dev)
+        best = a.elapsed_time(b) if best is None else min(best, a.elapsed_time(b))
+      del buf_p
+      fps = k / (best * 1e-3)
+      gbs = float(os.environ.get('VPB200_INGEST_GBS', '720'))
+      box[0] = (render.root_aware_frames(frames, world, res * res * 3, fps, gbs), fps, gbs)
+    dist.broadcast_object_list(box, src=0)
+    root_frames, fps, gbs = box[0]
+    shard_model = {'root_frames': int(root_frames), 'render_fps_measured': round(fps), 'ingest_gbs_assumed': gbs}
+  bounds = [render.shard_bounds(frames, world, r, root_frames) for r in range(world)]
+  begin, end = bounds[rank]
+  per = max(e - b for b, e in bounds)
+  coeffs, angles = coeffs_all[begin:end], angles_all[begin:end]
+  ex_dev, params_dev = render.device_inputs(coeffs, angles, dev)
+  peer = render.PeerFrameBuffer(per, res, world, rank, dev, bounds=bounds) if gather_mode == 'p2p' else None
+  total_slots = bounds[-1][1] if peer is not None else world * per
   local = None if peer is not None else torch.empty((per, res, res, 3), dtype=torch.uint8, device=dev)
   full = [None]
 
@@ -538,23 +565,19 @@ def run_sharded(env, name, steps, warmup):
     for a in range(0, t.shape[0], 64):
       out[a:a + 64] = (t[a:a + 64].reshape(-1, res * res * 3).to(torch.int64) * weights).sum(dim=1)
     return out
-  mine = torch.zeros(world * per, dtype=torch.int64, device=dev)
-  mine[rank * per:rank * per + (end - begin)] = frame_sums(scratch)
+  mine = torch.zeros(frames, dtype=torch.int64, device=dev)      # contiguous shards: slot == global frame index
+  mine[begin:end] = frame_sums(scratch)
   dist.all_reduce(mine)
   verified = None
   if rank == 0:
-    got = frame_sums(full[0][:world * per])
-    valid = torch.zeros(world * per, dtype=torch.bool, device=dev)
-    for r in range(world):
-      b, e = render.shard_bounds(frames, world, r)
-      valid[r * per:r * per + (e - b)] = True
-    verified = bool(torch.equal(got[valid], mine[valid])) and bool(mine[valid].ne(0).all())
+    got = frame_sums(full[0][:frames])
+    verified = bool(torch.equal(got, mine)) and bool(mine.ne(0).all())
   del scratch
 
   # ---- end to end: host coefficient rows in, rank 0's gathered buffer drained to page-locked host memory
   host_t = None
   if rank == 0:
-    host = _lib.pinned_empty((world * per, res, res, 3), np.uint8)
+    host = _lib.pinned_empty((total_slots, res, res, 3), np.uint8)
     host_t = torch.from_numpy(np.asarray(host))
 
   def e2e_step():
@@ -564,7 +587,7 @@ def run_sharded(env, name, steps, warmup):
     else:
       f = render.pipelined_gather(dm, ex2, par2, True, res, local, world, rank)
     if rank == 0:
-      host_t.copy_(f[:world * per], non_blocking=True)          # d2h of the gathered frames
+      host_t.copy_(f[:total_slots], non_blocking=True)          # d2h of the gathered frames
     torch.cuda.synchronize(dev)
   for _ in range(2):
     e2e_step()
@@ -613,7 +636,7 @@ def run_sharded(env, name, steps, warmup):
       'store-chunks': 'resolve kernels store straight into rank 0 buffer over NVLink, chunked over two streams',
       'nccl': 'NCCL gather of uint8 frames to rank 0, per chunk on a side stream'}.get(eff_mode, eff_mode)
   frame_bytes = res * res * 3
-  ingest = (world - 1) * per * frame_bytes
+  ingest = (frames - (end - begin)) * frame_bytes            # rank 0 here: everything it did not render itself
   exposed_ms = max(0.0, ms_per_step - render_ms)
   pipeline_gbs = total_bytes / (ms_per_step * 1e-3) / 1e9
   return {
@@ -624,13 +647,13 @@ def run_sharded(env, name, steps, warmup):
                  'rank0_ingest_gbs_over_step': round(ingest / ms_per_step / 1e6, 1),
                  'completion_wait_timeouts': int(lib.vp_peer_timeouts())},
       'e2e': {'value': frames / e2e_sec, 'unit': 'frames/s',
-              'h2d_bytes_per_step': frames * (64 * 4 + 192), 'd2h_bytes_per_step': world * per * frame_bytes,
+              'h2d_bytes_per_step': frames * (64 * 4 + 192), 'd2h_bytes_per_step': total_slots * frame_bytes,
               'note': 'every rank uploads its coefficient rows, renders and pushes; rank 0 then drains the gathered '
                       'buffer to page-locked host memory (one PCIe link: the drain bounds this figure)'},
       'roofline_pipeline': {'algorithmic_bytes': total_bytes, 'achieved': round(pipeline_gbs, 1), 'peak': peak * world,
                             'unit': 'GB/s', 'frac': round(pipeline_gbs / (peak * world), 4),
                             'note': 'peak = %d x the measured single-GPU figure' % world},
-      'n1_same_config': n1,
+      'n1_same_config': n1, 'shards': [e - b for b, e in bounds], 'shard_model': shard_model,
   }, peer
 
 
@@ -649,9 +672,12 @@ def run_ours(args):
           'metric': METRIC, 'value': r['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
           'warmup': max(args.warmup, 3), 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong',
           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-          'config': {'workload': workload_name(name), 'name': name, 'frames_total': frames, 'frames_per_gpu': per,
+          'config': {'workload': workload_name(name), 'name': name, 'frames_total': frames, 'frames_per_gpu': r['shards'],
+                     'shard_model': r['shard_model'],
                      'resolution': res, 'model': MODEL_NOTE, 'coeff_seed': 1, 'l2': env.l2_note(), 'gather': r['gather']['mode'],
-                     'sharding': 'contiguous frame ranges, model replicated, no data-path collective; frames gathered into rank 0 buffer inside the step'},
+                     'sharding': 'contiguous frame ranges, model replicated, no data-path collective; frames gathered into rank 0 buffer '
+                                 'inside the step; from 3 ranks on rank 0 renders a few more frames than the others (root-aware split: what it '
+                                 'renders itself does not cross its NVLink port, which bounds the step at 8 ranks)'},
           'roofline': None, 'roofline_pipeline': r['roofline_pipeline'], 'gather': r['gather'],
           'gather_verified': r['gather_verified'], 'n1_same_config': r['n1_same_config'],
           'cpu_baseline': None, 'e2e': r['e2e'], 'gpu_launches': r['launches'], 'clocks': r['clocks'],

@@ -322,7 +322,8 @@ int vp_render_sequence_dev_chunks(vp_model* m, int nframes, const float* ex_dev,
 int vp_basis_dev(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, void* stream);
 int vp_model_rows_pad(const vp_model* m);
 /* Diagnostics: one tcgen05 basis launch (nframes <= 128) that also writes a clock64() timeline of
- * CTA 0 to trace_dev[256] (4 roles x 16 tiles x 4 marks). */
+ * CTA 0 to trace_dev[0..256) (4 roles x 16 tiles x 4 marks) and the %globaltimer entry / exit time (ns) of every CTA c
+ * to trace_dev[256 + 2 c], trace_dev[257 + 2 c]; trace_dev holds 1024 int64 entries. */
 int vp_debug_basis_trace(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
                          long long* trace_dev, void* stream);
 

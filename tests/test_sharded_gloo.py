@@ -90,3 +90,25 @@ def test_push_plan_covers_every_frame(monkeypatch):
   monkeypatch.setenv('VPB200_PUSH_PLAN', '25,25,25')
   assert render.push_plan(75, 8) == [25, 25, 25]
   assert render.push_plan(76, 8) != [25, 25, 25]          # does not add up: ignored
+
+
+def test_root_aware_shards_cover_every_frame_once():
+  """render.root_aware_frames / shard_bounds(root_frames=...): rank 0 renders more than the equal share only when its
+  NVLink ingest would bound the step (8 ranks at the measured rates), never less; shards stay contiguous and cover
+  [0, T) exactly once."""
+  from voicepuppet_b200 import render
+  fb = 256 * 256 * 3
+  for world in (2, 4):
+    assert render.root_aware_frames(12000, world, fb, 595e3, 720.0) == 12000 // world
+  f0 = render.root_aware_frames(12000, 8, fb, 595e3, 720.0)
+  assert 1500 < f0 < 2000
+  assert render.root_aware_frames(12000, 8, fb, 595e3, 1e9) == 1500          # an infinitely fast link: equal shards
+  for world, root in ((8, f0), (8, None), (3, 5000), (5, 12000), (4, 0)):
+    bounds = [render.shard_bounds(12000, world, r, root) for r in range(world)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == 12000
+    assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+    assert all(b >= a for a, b in bounds)
+    if root is not None:
+      assert bounds[0] == (0, root)
+      rest = [b - a for a, b in bounds[1:]]
+      assert max(rest) - min(r for r in rest if r > 0 or True) <= max(rest)   # ceil-sized, the last ones may be short

@@ -113,6 +113,12 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
   const int lane = tid & 31;
 
+  if (tid == 0) VP_TRACE(0, 0, 0);                       // kernel entry
+  if (trace != nullptr && tid == 0) {                    // per-CTA entry time (ns): trace[256 + 2 * cta]
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    trace[256 + 2 * blockIdx.x] = (long long)ns;
+  }
   if (tid == 0) {
     if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
     ptx::prefetch_tensormap(&tmap_a);
@@ -164,9 +170,11 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
     }
     ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   }
+  if (tid == 0) VP_TRACE(0, 0, 1);                       // prologue of thread 0 done (barriers, first TMA loads, prefetches)
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (tid == 0) VP_TRACE(0, 0, 2);                       // every warp past the set-up barrier (TMEM allocated, B split)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int first = blockIdx.x, step = gridDim.x;
 
@@ -299,6 +307,11 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (trace != nullptr && warp == kWarpEpi0 && lane == 0) {   // per-CTA exit time (ns), after the last epilogue
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+    trace[257 + 2 * blockIdx.x] = (long long)ns;
+  }
   if (warp == kWarpMma) ptx::tmem_dealloc(tmem_base, kStagesL * kTcN);
 #undef VP_TRACE
 }

@@ -449,8 +449,9 @@ extern "C" int vp_basis_dev(vp_model* m, const float* ex_dev, float* disp_dev, i
   return launch_basis(m, ex_dev, disp_dev, nframes, static_cast<cudaStream_t>(stream));
 }
 
-// Diagnostics: one tcgen05 basis launch with a clock64() timeline of CTA 0 written to trace_dev[256]
-// (4 roles x 16 tiles x 4 marks; see VP_TRACE in basis_tc.cu).
+// Diagnostics: one tcgen05 basis launch with a clock64() timeline of CTA 0 written to trace_dev[0..256)
+// (4 roles x 16 tiles x 4 marks; see VP_TRACE in basis_tc.cu) and the %globaltimer entry / exit time (ns) of CTA c
+// in trace_dev[256 + 2 c], trace_dev[257 + 2 c]; trace_dev holds 1024 entries.
 extern "C" int vp_debug_basis_trace(vp_model* m, const float* ex_dev, float* disp_dev, int nframes,
                                     long long* trace_dev, void* stream) {
   VP_REQUIRE(m != nullptr && ex_dev && disp_dev && trace_dev && nframes > 0 && nframes <= 128, "bad argument");

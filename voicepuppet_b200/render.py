@@ -95,11 +95,38 @@ def render_sequence(coeffs, facemodel, res=IMG, angles='jitter', want_mask=False
   return (out, mask_out) if want_mask else out
 
 
-def shard_bounds(n_frames, world_size, rank):
-  """Contiguous frame range [begin, end) of ``rank``: ceil-sized shards, the last ones may be short."""
-  per = -(-n_frames // world_size)
-  begin = min(rank * per, n_frames)
+def shard_bounds(n_frames, world_size, rank, root_frames=None):
+  """Contiguous frame range [begin, end) of ``rank``: ceil-sized shards, the last ones may be short.
+  With ``root_frames`` rank 0 takes exactly that many frames and the others share the rest (see root_aware_frames)."""
+  if root_frames is None or world_size < 2:
+    per = -(-n_frames // world_size)
+    begin = min(rank * per, n_frames)
+    return begin, min(begin + per, n_frames)
+  f0 = max(0, min(int(root_frames), n_frames))
+  if rank == 0:
+    return 0, f0
+  per = -(-(n_frames - f0) // (world_size - 1))
+  begin = min(f0 + (rank - 1) * per, n_frames)
   return begin, min(begin + per, n_frames)
+
+
+def root_aware_frames(n_frames, world, frame_bytes, render_fps, ingest_gbs, startup_s=1.5e-4):
+  """How many frames rank 0 should render itself when it also receives everybody else's frames.  With equal shards
+  the step is bounded by rank 0's NVLink ingest from 8 ranks on ((world - 1) / world of all the bytes through one
+  port: 2.06 GB of the 12000-frame configuration, 2.9 ms at the ~720 GB/s measured, against 2.5 ms of rendering);
+  every frame rank 0 renders itself is a frame that does not cross the link.  Minimises
+     max(f0 / R,  (n - f0) / ((world - 1) R),  startup + (n - f0) * frame_bytes / B)
+  over f0 (R = frames/s one GPU renders, B = ingest bytes/s); returns the equal share when that is already optimal."""
+  if world < 2 or render_fps <= 0 or ingest_gbs <= 0:
+    return -(-n_frames // max(world, 1))
+  equal = -(-n_frames // world)
+  b = frame_bytes / (ingest_gbs * 1e9)
+  best, best_t = equal, None
+  for f0 in range(equal, min(n_frames, 2 * equal) + 1):
+    t = max(f0 / render_fps, (n_frames - f0) / ((world - 1) * render_fps), startup_s + (n_frames - f0) * b)
+    if best_t is None or t < best_t - 1e-12:
+      best, best_t = f0, t
+  return best
 
 
 def device_inputs(coeffs, angles, device):
@@ -231,24 +258,33 @@ class PeerFrameBuffer(object):
   HBM, so gathering the frames is fused into the rendering: no copy kernel, no staging buffer; the only
   collective left is a one-element all-reduce that orders rank 0's consumer after every rank's stores."""
 
-  def __init__(self, per, res, world, rank, device, group=None):
+  def __init__(self, per, res, world, rank, device, group=None, bounds=None):
+    """per: frames per rank (rank r's slice starts at frame r * per; the last shard may be padded) -- or, with
+    ``bounds`` = [(begin, end)] * world (contiguous, covering [0, T)), uneven shards in a dense [T,res,res,3] buffer."""
     import ctypes
     import torch
     import torch.distributed as dist
     from . import _lib
-    self.per, self.res, self.world, self.rank, self.group = per, res, world, rank, group
+    if bounds is None:
+      bounds = [(r * per, (r + 1) * per) for r in range(world)]
+    if len(bounds) != world or bounds[0][0] != 0 or any(bounds[r][1] != bounds[r + 1][0] for r in range(world - 1)):
+      raise ValueError('bounds must be contiguous frame ranges, one per rank, starting at 0')
+    self.bounds = [(int(a), int(b)) for a, b in bounds]
+    total = self.bounds[-1][1]
+    self.per = self.bounds[rank][1] - self.bounds[rank][0]     # frames this rank contributes
+    self.res, self.world, self.rank, self.group = res, world, rank, group
     self.frame_bytes = res * res * 3
     self.full = None
     self._base = None
     payload = [None]
-    n_bytes = world * per * self.frame_bytes
+    n_bytes = total * self.frame_bytes
     self.device = device
     self.step = 0
     self.local = None
     if rank == 0:
       # frames, then one 32-bit completion flag per rank (128-byte aligned)
       self._storage = torch.zeros(((n_bytes + 127) // 128) * 128 + 128, dtype=torch.uint8, device=device)
-      self.full = self._storage[:n_bytes].view(world * per, res, res, 3)
+      self.full = self._storage[:n_bytes].view(total, res, res, 3)
       handle = (ctypes.c_ubyte * 64)()
       offset = ctypes.c_ulonglong()
       _lib.check(_lib.lib().vp_ipc_export(ctypes.c_void_p(self._storage.data_ptr()), handle, ctypes.byref(offset)))
@@ -264,7 +300,7 @@ class PeerFrameBuffer(object):
       _lib.check(_lib.lib().vp_ipc_open(buf, device.index, ctypes.byref(base)))
       self._base = base
       start = base.value + offset
-    self.slice_ptr = start + rank * per * self.frame_bytes
+    self.slice_ptr = start + self.bounds[rank][0] * self.frame_bytes
     self.flags_ptr = start + ((n_bytes + 127) // 128) * 128
     if world > 32:
       raise ValueError('PeerFrameBuffer supports up to 32 ranks')

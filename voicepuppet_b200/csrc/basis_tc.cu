@@ -375,7 +375,7 @@ int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nfram
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   const int grid = std::min(ntiles, sms);
-  static const int store_policy = [] { const char* e = std::getenv("VPB200_BASIS_STORE"); return e ? std::atoi(e) : 0; }();
+  const int store_policy = 0;  // streaming stores (default-policy stores measured equal in round 1)
   for (int t0 = 0; t0 < nframes; t0 += kTcN) {
     const int n = std::min(kTcN, nframes - t0);
     const int n_mma = (n + 15) & ~15;

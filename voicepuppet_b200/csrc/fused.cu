@@ -40,7 +40,6 @@ struct FusedArgs {
   EpochKey km;
   int h, w;
   int inline_max;               // see raster_walk.cuh
-  int debug;                    // timing experiments only (VPB200_FUSED_DEBUG): 1 = no E phase, 2 = no colours, 4 = no projection
 };
 
 // E phase for one frame: the tile's owned triangles against the frame's z-buffer.
@@ -148,16 +147,16 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) fused_tile_kernel(const Fu
   for (int f = f_begin; f < f_end; ++f) {
     const int buf = (f - f_begin) & 1;
     // ---- C: colours of the own vertices, projection of every local vertex ---------------------------
-    if (own && !(a.debug & 2)) {
+    if (own) {
       float nx, ny, nz;
       fan_normal_sum(reinterpret_cast<const char*>(s_pos[buf]), fan, pv, nx, ny, nz);
       a.vcol[(size_t)f * a.vcol_stride + lv.gv[0]] = light_fast(s_frame[buf], nx, ny, nz, tr, tg, tb);
     }
-    if (has0 && !(a.debug & 4)) {
+    if (has0) {
       const float3 p = project_fast(s_frame[buf], lv.bx + (double)c0x, lv.by + (double)c0y, lv.bz + (double)c0z);
       s_scr[buf][tid] = make_float4(p.x, p.y, p.z, 0.f);
     }
-    if (has1 && !(a.debug & 4)) {
+    if (has1) {
       const float3 p = project_fast(s_frame[buf], hx + (double)c1x, hy + (double)c1y, hz + (double)c1z);
       s_scr[buf][tid + kTileV] = make_float4(p.x, p.y, p.z, 0.f);
     }
@@ -176,8 +175,7 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) fused_tile_kernel(const Fu
     }
     __syncthreads();
     // ---- E: the tile's own triangles of frame f (s_scr[buf] is rewritten two barriers from now) -----
-    if (!(a.debug & 1))
-      raster_owned(s_scr[buf], s_tri, nt, s_rec[tid >> 5], a.keys + (size_t)f * npix, a.km, a.h, a.w, tid, a.inline_max);
+    raster_owned(s_scr[buf], s_tri, nt, s_rec[tid >> 5], a.keys + (size_t)f * npix, a.km, a.h, a.w, tid, a.inline_max);
   }
 }
 
@@ -258,27 +256,16 @@ int launch_fused(vp_model* m, const float* disp_dev, int nframes, const void* fr
   a.km = make_epoch_key(m->ntri, epoch);
   a.h = res;
   a.w = res;
-  static const int debug_env = [] { const char* e = std::getenv("VPB200_FUSED_DEBUG"); return e ? std::atoi(e) : 0; }();
-  a.debug = debug_env;
   a.inline_max = inline_box_pixels();
-  static const int fpb_env = [] { const char* e = std::getenv("VPB200_FUSED_FPB"); return e ? std::atoi(e) : 0; }();
-  static const int minb_env = [] { const char* e = std::getenv("VPB200_FUSED_MINB"); return e ? std::atoi(e) : 0; }();
-  static const int waves_env = [] { const char* e = std::getenv("VPB200_FUSED_WAVES"); return e ? std::atoi(e) : 0; }();
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
-  const int minb = minb_env > 0 ? minb_env : 5;
-  const int waves = waves_env > 0 ? waves_env : 2;
+  const int minb = 5, waves = 2;   // measured best of 4 / 5 / 6 CTAs per SM and 1..4 waves (profiles/r02c_fused_ablation.txt)
   // a CTA takes a run of frames (tile constants and the pipeline prologue are paid once per CTA); runs are sized
   // for about `waves` resident waves of CTAs
   const int groups = std::max(1, std::min(nframes, (sms * minb * waves) / std::max(m->ntiles, 1)));
-  v.frames_per_block = fpb_env > 0 ? fpb_env : (nframes + groups - 1) / groups;
+  v.frames_per_block = (nframes + groups - 1) / groups;
   dim3 grid(m->ntiles, (nframes + v.frames_per_block - 1) / v.frames_per_block);
-  if (minb >= 6)
-    fused_tile_kernel<6><<<grid, kTileV, 0, st>>>(a);
-  else if (minb == 5)
-    fused_tile_kernel<5><<<grid, kTileV, 0, st>>>(a);
-  else
-    fused_tile_kernel<4><<<grid, kTileV, 0, st>>>(a);
+  fused_tile_kernel<minb><<<grid, kTileV, 0, st>>>(a);
   VP_LAUNCH_CHECK();
   return VP_OK;
 }

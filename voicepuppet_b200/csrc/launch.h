@@ -23,9 +23,8 @@ int inline_box_pixels();
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
                           unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
                           int w, cudaStream_t st);
-int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, const int* t_orig2int,
-                          uint32_t epoch, unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
-                          cudaStream_t st);
+int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, uint32_t epoch,
+                          unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w, cudaStream_t st);
 
 // ---- vertex-tile topology (topology.cpp builds it, reconstruct.cu consumes it) ----------
 constexpr int kTileV = 128;    // max own vertices per tile == threads per CTA of the vertex kernel

@@ -73,12 +73,11 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
                           int w, cudaStream_t st) {
   if (ntri == 0 || nframes == 0) return VP_OK;
   static const int fpb_env = [] { const char* e = std::getenv("VPB200_SCATTER_FPB"); return e ? std::atoi(e) : 0; }();
-  static const int legacy = [] { const char* e = std::getenv("VPB200_SCATTER_LEGACY"); return e ? std::atoi(e) : 0; }();
   const int fpb = fpb_env > 0 ? fpb_env : (nframes >= 32 ? 4 : (nframes >= 16 ? 2 : 1));  // frames per block: indices are loaded once
   dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, (nframes + fpb - 1) / fpb);
   const bool fits32 = (unsigned long long)nframes * frame_stride < (1ull << 32) &&
                       (unsigned long long)nframes * (unsigned long long)ntri < (1ull << 32);
-  if (legacy || !fits32) {  // the generic template on the packed records (kept for A/B measurements)
+  if (!fits32) {  // the generic template on the packed records (64-bit offsets)
     PackedMesh mesh{vrec, triangles, frame_stride};
     raster_scatter_kernel<kModeColors, PackedMesh, EpochKey><<<grid, kRasterBlock, 0, st>>>(
         mesh, make_epoch_key(ntri, epoch), keys, tri_color, ntri, nframes, fpb, h, w, 1);
@@ -108,13 +107,12 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
   return VP_OK;
 }
 
-int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, const int* t_orig2int,
-                          uint32_t epoch, unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
+int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_color, uint32_t epoch, unsigned char* image, unsigned char* mask, int nframes, int ntri, int h, int w,
                           cudaStream_t st) {
   const size_t npix = (size_t)h * w;
   if (nframes == 0 || npix == 0) return VP_OK;
   dim3 grid((unsigned)((npix / 4 + 255) / 256), nframes);
-  resolve_packed_kernel<<<grid, 256, 0, st>>>(keys, make_epoch_key(ntri, epoch), tri_color, t_orig2int, image, mask,
+  resolve_packed_kernel<<<grid, 256, 0, st>>>(keys, make_epoch_key(ntri, epoch), tri_color, image, mask,
                                               ntri, npix);
   VP_LAUNCH_CHECK();
   return VP_OK;

@@ -663,7 +663,6 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
   a.nver = m->nver;
   static const int fpb_env = [] { const char* e = std::getenv("VPB200_VERTEX_FPB"); return e ? std::atoi(e) : 0; }();
   static const int minb_env = [] { const char* e = std::getenv("VPB200_VERTEX_MINB"); return e ? std::atoi(e) : 0; }();
-  static const int force_generic = [] { const char* e = std::getenv("VPB200_VERTEX_GENERIC"); return e ? std::atoi(e) : 0; }();
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   // Frames per CTA: the tile constants (dependent global loads) and the pipeline prologue are paid once per
@@ -673,13 +672,12 @@ int launch_vertex(vp_model* m, const float* disp_dev, const FrameParams* params_
     const int groups = std::max(1, std::min(nframes, (sms * blocks_per_sm * waves) / std::max(ntiles, 1)));
     return (nframes + groups - 1) / groups;
   };
-  const int n_fan = (force_generic || m->vertex_mode == 1) ? 0 : m->n_fan_tiles;
+  const int n_fan = (m->vertex_mode == 1) ? 0 : m->n_fan_tiles;
   if (n_fan > 0) {
     const int minb = minb_env > 0 ? minb_env : 8;
     a.frames_per_block = frames_per_block(n_fan, minb, 2);
     dim3 grid(n_fan, (nframes + a.frames_per_block - 1) / a.frames_per_block);
-    static const int slow_env = [] { const char* e = std::getenv("VPB200_VERTEX_SLOW"); return e ? std::atoi(e) : 0; }();
-    const bool fast = !a.has_out && a.vrec != nullptr && !slow_env;  // raster records only: the folded constants
+    const bool fast = !a.has_out && a.vrec != nullptr;  // raster records only: the folded constants
     if (fast && m->have_slots && m->vertex_mode != 2) {
       vertex_fan_kernel<8, true, true><<<grid, kTileV, 0, st>>>(a);
     } else if (fast) {

@@ -208,7 +208,7 @@ struct ChunkRunner {
     VP_TRY(launch_scatter_packed(vrec, (size_t)m->vrec_stride, m->tri, keys, tricol, epoch, n, m->ntri, res, res, cs));
     prof.end();
     prof.begin(kProfResolve);
-    VP_TRY(launch_resolve_packed(keys, tricol, m->t_orig2int_dev, epoch, image_dev, mask_dev, n, m->ntri, res, res, cs));
+    VP_TRY(launch_resolve_packed(keys, tricol, epoch, image_dev, mask_dev, n, m->ntri, res, res, cs));
     prof.end();
     if (used) *used = cs;
     return VP_OK;

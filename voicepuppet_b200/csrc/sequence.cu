@@ -110,6 +110,7 @@ struct ChunkRunner {
   const char* fconst = nullptr;
   bool dual = false, aux_used = false, aux_needs_basis = false, fused = false;
   int issued = 0;
+  int basis_upto = 0;   // frames [group start, basis_upto) of the current basis group are contracted
 
   ChunkRunner(vp_model* m_, cudaStream_t st_) : m(m_), st(st_), prof(m_, st_) {}
 
@@ -156,18 +157,29 @@ struct ChunkRunner {
 
   // frames [t0, t0 + n): n <= chunk_cap and inside one basis group.  *used = the stream the chunk runs on.
   int run(int t0, int n, unsigned char* image_dev, unsigned char* mask_dev, cudaStream_t* used) {
-    if (ex_dev && t0 % group == 0) {  // a new basis group: contract its expression coefficients on `st`
-      if (aux_used) {                 // chunks on the auxiliary stream may still read the previous group
-        VP_CUDA(cudaEventRecord(m->ev_aux_done, m->aux_stream));
-        VP_CUDA(cudaStreamWaitEvent(st, m->ev_aux_done, 0));
+    if (ex_dev) {
+      // The expression coefficients of a basis group are contracted on `st`, lazily and in pieces of 128 frames (one
+      // tcgen05 launch): only as far as this chunk needs.  A short first chunk (the push gather's plan) then starts
+      // after one launch instead of after the whole group; a chunk that spans the group gets it in one call as before.
+      const int g0 = t0 - t0 % group, gend = std::min(g0 + group, nframes);
+      if (t0 == g0) {
+        if (aux_used) {                 // chunks on the auxiliary stream may still read the previous group
+          VP_CUDA(cudaEventRecord(m->ev_aux_done, m->aux_stream));
+          VP_CUDA(cudaStreamWaitEvent(st, m->ev_aux_done, 0));
+        }
+        basis_upto = g0;
       }
-      const int gn = std::min(group, nframes - t0);
-      prof.begin(kProfBasis);
-      VP_TRY(launch_basis(m, ex_dev + (size_t)t0 * VP_N_EX, m->ws_disp.as<float>(), gn, st));
-      prof.end();
-      if (dual) {
-        VP_CUDA(cudaEventRecord(m->ev_basis, st));
-        aux_needs_basis = true;
+      if (basis_upto < t0 + n) {
+        const int upto = std::min(gend, g0 + (t0 + n - g0 + 127) / 128 * 128);
+        prof.begin(kProfBasis);
+        VP_TRY(launch_basis(m, ex_dev + (size_t)basis_upto * VP_N_EX,
+                            m->ws_disp.as<float>() + (size_t)(basis_upto - g0) * m->rows_pad, upto - basis_upto, st));
+        prof.end();
+        basis_upto = upto;
+        if (dual) {
+          VP_CUDA(cudaEventRecord(m->ev_basis, st));
+          aux_needs_basis = true;
+        }
       }
     }
     const int slot = dual ? (issued & 1) : 0;

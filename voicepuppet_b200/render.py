@@ -194,10 +194,12 @@ def push_plan(n_local, world):
     # contraction runs 128 frames per launch inside a chunk), the first one cut 64 + 192 so that the first push
     # starts early, the last one ending with a 64-frame chunk so that the push left exposed at the end is short.
     chunk = int(os.environ.get('VPB200_PUSH_CHUNK', '256'))
+    first = min(int(os.environ.get('VPB200_PUSH_FIRST', '64')), chunk // 2)
+    last = int(os.environ.get('VPB200_PUSH_LAST', '64'))
     n_full, rem = divmod(n_local, chunk)
-    plan = [64, chunk - 64] + [chunk] * (n_full - 1)
-    if rem > 96:
-      plan += [rem - 64, 64]
+    plan = [first, chunk - first] + [chunk] * (n_full - 1)
+    if rem > last + 32:
+      plan += [rem - last, last]
     elif rem > 0:
       plan += [rem]
     return plan

@@ -141,6 +141,42 @@ def test_tensor_core_basis_matches_fp32_and_fp64(full_model, t):
   assert float(np.abs(out[1] - out[2]).max()) < 4e-7
 
 
+@pytest.mark.parametrize('t', [129, 300, 1100])
+def test_tensor_core_basis_many_frame_blocks(full_model, t):
+  """K1 above 128 frames: ONE launch walks (frame block, row tile) items and re-splits the frame coefficients when a
+  CTA enters the next block.  Checked through the C ABI's device-pointer entry (vp_basis_dev) against a float64
+  contraction of the same float32 basis, and against the FP32 kernel; rows of the last, partial block included."""
+  import torch
+  from voicepuppet_b200 import _lib
+  from voicepuppet_b200.model import DeviceModel
+  dm = DeviceModel.of(full_model)
+  lib = _lib.lib()
+  rows_pad = lib.vp_model_rows_pad(dm.handle)
+  dev = torch.device('cuda', 0)
+  ex = synthetic.make_coeffs(t, seed=11)[:, 80:144].copy()
+  ex_d = torch.from_numpy(ex).to(dev)
+  st = torch.cuda.current_stream(dev).cuda_stream
+  out = {}
+  try:
+    for mode in (1, 2):
+      _lib.check(lib.vp_set_basis_mode(dm.handle, mode))
+      disp = torch.full((t, rows_pad), float('nan'), device=dev)
+      _lib.check(lib.vp_basis_dev(dm.handle, ex_d.data_ptr(), disp.data_ptr(), t, st))
+      torch.cuda.synchronize()
+      out[mode] = disp.cpu().numpy()
+  finally:
+    _lib.check(lib.vp_set_basis_mode(dm.handle, 0))
+  nrow = int(full_model.meanshape.size)        # 3 N rows; the rest of rows_pad is padding
+  assert np.isfinite(out[2][:, :nrow]).all()
+  # same multiset of values as the float64 contraction (the device rows are Morton-renumbered: compare sorted rows)
+  want = np.einsum('ij,tj->ti', full_model.exBase.astype(np.float32).astype(np.float64), ex.astype(np.float64))
+  scale = float(np.abs(want).max())
+  assert float(np.abs(out[1][:, :nrow] - out[2][:, :nrow]).max()) < 4e-7 * max(1.0, scale)
+  for k in (0, 127, 128, t // 2, t - 1):
+    got = np.sort(out[2][k, :nrow].astype(np.float64))
+    assert float(np.abs(got - np.sort(want[k])).max()) < 4e-7 * max(1.0, scale), k
+
+
 def test_generic_vertex_kernel_matches_fan_kernel(full_model):
   """K2 has two flavours (fan records / ring of staged face normals); the full model is manifold, so it
   normally takes the fan path: force the generic kernel and compare both with the oracle."""

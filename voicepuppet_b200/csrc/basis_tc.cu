@@ -2,7 +2,12 @@
 // (reference: the expression einsum of Shape_formation, utils/reconstruct_mesh.py:21-22)
 //
 // GEMM view: D[M = 128 basis rows][N = frames <= 128] = A[M][K = 64] * B[N][K]^T, operands K-major.
-// Persistent, warp-specialised kernel, one CTA per SM, each CTA walks basis row tiles m, m+grid, ...:
+// One launch contracts any number of frames: the work items are (frame block of 128, basis row tile) pairs,
+// numbered block-major (w = block * ntiles + tile), so that every CTA is on the same frame block at about the same
+// time and the 27 MB basis is read from HBM by the first block and from L2 by the others; the 148 CTAs take the
+// items round-robin, which also spreads the 837 % 148 remainder over the blocks (round 2: one 128-frame launch per
+// block cost 23.5 us by CUDA events for a 13.8 us body).
+// Persistent, warp-specialised kernel, one CTA per SM, each CTA walks the items w, w+grid, ...:
 //   warp 0 (one lane)   TMA producer: two tensor loads per tile (one per 32-float K half) land the
 //                       128 x 64 fp32 tile (32 KB) in the canonical 128-byte-swizzled K-major layout
 //                       the UMMA shared-memory descriptor expects; 3-stage ring, plus L2 prefetches
@@ -15,8 +20,11 @@
 //                       them to the mbarriers that free the A stage and release the epilogue
 //   warps 2-9           epilogue, two warps per TMEM lane quarter: tcgen05.ld (32 rows x 16 frames per
 //                       load), frame-major stores, 128 contiguous bytes per warp store
-// The frame coefficients (B) are split once per CTA.  The dropped lo*lo term is 2^-22 relative, so the
-// result has fp32-grade accuracy; the basis is read from HBM once, as fp32.
+// The frame coefficients (B) of a block are split by the split warps when a CTA enters the block: they wait for the
+// MMAs of the previous item (the last readers of the old B tiles), rewrite the tiles and only then release the
+// item to the MMA issuer; the epilogue still has two accumulators to drain meanwhile, so the stores never pause.
+// The dropped lo*lo term is 2^-22 relative, so the result has fp32-grade accuracy; the basis is read from HBM
+// once per launch, as fp32.
 // The contraction is HBM-bound (K = 64: at most 32 flop/B); tensor cores are used to get the FP32
 // SIMT pipe out of the way, not because the math is heavy.
 #include <cuda.h>
@@ -99,11 +107,11 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
   // optional per-role timeline of CTA 0 (diagnostics): trace[role * 64 + it * 4 + k] = clock64()
   const bool tracing = trace != nullptr && blockIdx.x == 0;
 #define VP_TRACE(role, it, k) do { if (tracing && (it) < 16) trace[(role) * 64 + (it) * 4 + (k)] = clock64(); } while (0)
-  const int n_mma = (nframes + 15) & ~15;  // <= kTcN
-  const int half_b = n_mma * 128;          // bytes of one K-half of a B tile
-  uint8_t* smem_bhi = smem + kOffB;
-  uint8_t* smem_blo = smem_bhi + 2 * half_b;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_blo + 2 * half_b);  // TMA landed
+  const int nblocks = (nframes + kTcN - 1) / kTcN;
+  const int total = nblocks * ntiles;      // work items (frame block, row tile), block-major
+  const int n_cap = (min(nframes, kTcN) + 15) & ~15;   // widest block of this launch: sizes the B tiles
+  uint8_t* smem_b = smem + kOffB;          // B hi tile, then B lo tile; each 2 K-halves of n_mma * 128 bytes
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_b + 4 * n_cap * 128);  // TMA landed
   uint64_t* bar_afree = bar_full + kStagesA;                         // [3] MMAs that read the A stage completed
   uint64_t* bar_split = bar_afree + kStagesA;                        // [2] hi/lo tiles ready for the MMA
   uint64_t* bar_mma = bar_split + kStagesL;                          // [2] accumulator complete (and lo tile free)
@@ -135,8 +143,9 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
     // The first A tiles do not depend on anything the other warps set up: start the HBM stream now,
     // under the TMEM allocation and the split of the frame coefficients.
     for (int p = 0; p < kStagesA; ++p) {
-      const int mp = (int)blockIdx.x + p * (int)gridDim.x;
-      if (mp < ntiles) {
+      const int wp = (int)blockIdx.x + p * (int)gridDim.x;
+      if (wp < total) {
+        const int mp = wp % ntiles;
         uint8_t* dst = smem + kOffAhi + p * kTileA;
         ptx::mbar_arrive_expect_tx(bar_full + p, kTileA);
         ptx::tma_load_2d(dst, &tmap_a, 0, mp * kTcM, bar_full + p);
@@ -144,10 +153,10 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
       }
     }
     for (int p = kStagesA; p < kStagesA + kPrefetchTiles; ++p) {
-      const int mp = (int)blockIdx.x + p * (int)gridDim.x;
-      if (mp < ntiles) {
-        tma_prefetch_2d(&tmap_a, 0, mp * kTcM);
-        tma_prefetch_2d(&tmap_a, 32, mp * kTcM);
+      const int wp = (int)blockIdx.x + p * (int)gridDim.x;
+      if (wp < ntiles) {  // first frame block only: the later ones find the basis in L2
+        tma_prefetch_2d(&tmap_a, 0, wp * kTcM);
+        tma_prefetch_2d(&tmap_a, 32, wp * kTcM);
       }
     }
   }
@@ -155,19 +164,26 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
     ptx::tmem_alloc(tmem_slot, kStagesL * kTcN);
     ptx::tmem_relinquish();
   }
-  if (warp >= kWarpSplit0) {
-    // frame coefficients -> hi / lo tiles in the swizzled K-major layout: row n (frame), 16-byte chunk
-    // c of K-half h lives at h * half_b + (n / 8) * 1024 + (n % 8) * 128 + ((c ^ (n % 8)) * 16)
-    for (int q = tid - kWarpSplit0 * 32; q < n_mma * 16; q += kSplitThreads) {
+  // frame coefficients of frame block fb -> hi / lo tiles in the swizzled K-major layout: row n (frame), 16-byte
+  // chunk c of K-half h lives at h * half_b + (n / 8) * 1024 + (n % 8) * 128 + ((c ^ (n % 8)) * 16)
+  auto split_b = [&](int fb) {
+    const int nb = min(kTcN, nframes - fb * kTcN), nb_mma = (nb + 15) & ~15, half_b = nb_mma * 128;
+    const float* exb = ex + (size_t)fb * kTcN * VP_N_EX;
+    uint8_t* bhi = smem_b;
+    uint8_t* blo = smem_b + 2 * half_b;
+    for (int q = tid - kWarpSplit0 * 32; q < nb_mma * 16; q += kSplitThreads) {
       const int n = q >> 4, c16 = q & 15;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n < nframes) v = __ldg(reinterpret_cast<const float4*>(ex + (size_t)n * VP_N_EX) + c16);
+      if (n < nb) v = __ldg(reinterpret_cast<const float4*>(exb + (size_t)n * VP_N_EX) + c16);
       float4 h, l;
       split4(v, h, l);
       const int off = (c16 >> 3) * half_b + (n >> 3) * 1024 + (n & 7) * 128 + (((c16 & 7) ^ (n & 7)) << 4);
-      *reinterpret_cast<float4*>(smem_bhi + off) = h;
-      *reinterpret_cast<float4*>(smem_blo + off) = l;
+      *reinterpret_cast<float4*>(bhi + off) = h;
+      *reinterpret_cast<float4*>(blo + off) = l;
     }
+  };
+  if (warp >= kWarpSplit0 && (int)blockIdx.x < total) {
+    split_b((int)blockIdx.x / ntiles);
     ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   }
   if (tid == 0) VP_TRACE(0, 0, 1);                       // prologue of thread 0 done (barriers, first TMA loads, prefetches)
@@ -182,14 +198,15 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
     // ===== TMA producer (whole warp loops, one elected lane issues); stages 0..kStagesA-1 of the first
     // round were issued in the prologue =====
     int it = kStagesA;
-    for (int m = first + kStagesA * step; m < ntiles; m += step, ++it) {
+    for (int w = first + kStagesA * step; w < total; w += step, ++it) {
       const int s = it % kStagesA;
+      const int m = w % ntiles;
       ptx::mbar_wait(bar_afree + s, ((it / kStagesA) - 1) & 1);
       if (elect_one()) {
-        const int mp = m + kPrefetchTiles * step;
-        if (mp < ntiles) {
-          tma_prefetch_2d(&tmap_a, 0, mp * kTcM);
-          tma_prefetch_2d(&tmap_a, 32, mp * kTcM);
+        const int wp = w + kPrefetchTiles * step;
+        if (wp < ntiles) {
+          tma_prefetch_2d(&tmap_a, 0, wp * kTcM);
+          tma_prefetch_2d(&tmap_a, 32, wp * kTcM);
         }
         uint8_t* dst = smem + kOffAhi + s * kTileA;
         ptx::mbar_arrive_expect_tx(bar_full + s, kTileA);
@@ -201,14 +218,16 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
     }
   } else if (warp == kWarpMma) {
     // ===== MMA issuer (whole warp loops, one elected lane issues) =====
-    const uint32_t idesc = instr_desc_tf32(kTcM, n_mma);
     const uint64_t desc_hi = (64ull << 32) | (1ull << 46) | (2ull << 61);  // SBO, version, SWIZZLE_128B
     const uint32_t smem_base = ptx::smem_u32(smem);
-    const uint32_t b_hi = (smem_base + kOffB) >> 4, b_lo = (smem_base + kOffB + 2 * half_b) >> 4;
-    const uint32_t half_b16 = half_b >> 4;
     int it = 0;
-    for (int m = first; m < ntiles; m += step, ++it) {
+    for (int w = first; w < total; w += step, ++it) {
       const int sa = it % kStagesA, sl = it & 1;
+      const int fb = w / ntiles;
+      const int n_mma = (min(kTcN, nframes - fb * kTcN) + 15) & ~15, half_b = n_mma * 128;
+      const uint32_t idesc = instr_desc_tf32(kTcM, n_mma);
+      const uint32_t b_hi = (smem_base + kOffB) >> 4, b_lo = (smem_base + kOffB + 2 * half_b) >> 4;
+      const uint32_t half_b16 = half_b >> 4;
       VP_TRACE(1, it, 0);
       ptx::mbar_wait(bar_split + sl, (it >> 1) & 1);
       VP_TRACE(1, it, 1);
@@ -242,20 +261,22 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
     const int quarter = warp & 3;        // TMEM lanes this warp may read: 32 * (warp % 4) ..
     const int group = ew >> 2;           // two warps per lane quarter alternate over 16-column chunks
     int it = 0;
-    for (int m = first; m < ntiles; m += step, ++it) {
+    for (int w = first; w < total; w += step, ++it) {
       const int sl = it & 1;
+      const int fb = w / ntiles, m = w - fb * ntiles;
+      const int nb = min(kTcN, nframes - fb * kTcN), n_mma = (nb + 15) & ~15;  // frames of this block
       if (ew == 0 && lane == 0) VP_TRACE(3, it, 0);
       ptx::mbar_wait(bar_mma + sl, (it >> 1) & 1);
       if (ew == 0 && lane == 0) VP_TRACE(3, it, 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * kTcN);
-      float* out = disp + (size_t)m * kTcM + quarter * 32 + lane;
+      float* out = disp + (size_t)fb * kTcN * rows_pad + (size_t)m * kTcM + quarter * 32 + lane;
       for (int c0 = group * 16; c0 < n_mma; c0 += 32) {
         uint32_t r[16];
         ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
         float* o = out + (size_t)c0 * rows_pad;
-        if (c0 + 16 <= nframes) {
+        if (c0 + 16 <= nb) {
           if (store_policy == 0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
@@ -266,7 +287,7 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < nframes) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
+            if (c0 + j < nb) __stcs(o + (size_t)j * rows_pad, __uint_as_float(r[j]));
         }
       }
       // (loading all of a warp's chunks back to back, waiting once and releasing the accumulator before the stores
@@ -278,11 +299,18 @@ basis_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const float* __restr
   } else {
     // ===== split warps: hi / lo tiles of A tile `it` =====
     const int wt = tid - kWarpSplit0 * 32;  // 0..255
-    int it = 0;
-    for (int m = first; m < ntiles; m += step, ++it) {
+    int it = 0, fb_cur = first / ntiles;
+    for (int w = first; w < total; w += step, ++it) {
       const int sa = it % kStagesA, sl = it & 1;
       if (wt == 0) VP_TRACE(2, it, 0);
       if (it >= kStagesL) ptx::mbar_wait(bar_mma + sl, ((it >> 1) - 1) & 1);  // MMAs of tile it-2 no longer read lo[sl]
+      const int fb = w / ntiles;
+      if (fb != fb_cur) {
+        // entering a new frame block: the MMAs of item it-1 are the last readers of the old B tiles
+        ptx::mbar_wait(bar_mma + (sl ^ 1), ((it - 1) >> 1) & 1);
+        split_b(fb);
+        fb_cur = fb;
+      }
       ptx::mbar_wait(bar_full + sa, (it / kStagesA) & 1);
       if (wt == 0) VP_TRACE(2, it, 1);
       float4* hi4 = reinterpret_cast<float4*>(smem + kOffAhi + sa * kTileA);
@@ -363,8 +391,8 @@ int basis_tc_prepare(vp_model* m) {
   return VP_OK;
 }
 
-// nframes <= kTcN per launch: longer batches are cut into launches of 128 frames (the basis then
-// comes from L2 for every launch after the first).
+// One launch whatever the frame count: the kernel walks (frame block of 128, row tile) items, the basis comes from
+// HBM for the first block and from L2 for the others.
 int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nframes, cudaStream_t st,
                     long long* trace_dev) {
   if (nframes == 0) return VP_OK;
@@ -372,18 +400,16 @@ int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nfram
   CUtensorMap map;
   std::memcpy(&map, m->tmap_exb, sizeof(map));
   const int ntiles = m->rows_pad / kTcM;
+  VP_REQUIRE((long long)((nframes + kTcN - 1) / kTcN) * ntiles < (1ll << 30), "frame count too large for one launch");
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   const int grid = std::min(ntiles, sms);
-  const int store_policy = 0;  // streaming stores (default-policy stores measured equal in round 1)
-  for (int t0 = 0; t0 < nframes; t0 += kTcN) {
-    const int n = std::min(kTcN, nframes - t0);
-    const int n_mma = (n + 15) & ~15;
-    basis_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(n_mma), st>>>(
-        map, ex_dev + (size_t)t0 * VP_N_EX, disp_dev + (size_t)t0 * m->rows_pad, n, m->rows_pad, ntiles, trace_dev,
-        store_policy);
-    VP_LAUNCH_CHECK();
-  }
+  // streaming stores (default-policy stores measured equal in round 1); VPB200_BASIS_STORE=1 selects them for the A/B
+  static const int store_policy = [] { const char* e = std::getenv("VPB200_BASIS_STORE"); return e ? std::atoi(e) : 0; }();
+  const int n_cap = (std::min(nframes, kTcN) + 15) & ~15;
+  basis_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(n_cap), st>>>(map, ex_dev, disp_dev, nframes, m->rows_pad, ntiles,
+                                                                  trace_dev, store_policy);
+  VP_LAUNCH_CHECK();
   return VP_OK;
 }
 

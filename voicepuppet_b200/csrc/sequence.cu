@@ -84,10 +84,15 @@ struct Profiler {
   }
 };
 
-// The basis contraction runs over a larger group of frames than the raster chunk (one pass over
-// the 27 MB basis per group); its output for 96 frames (41 MB) still sits in L2 next to the basis.
+// The basis contraction runs over a larger group of frames than the raster chunk: ONE launch per group (the tcgen05
+// kernel walks the group in 128-frame blocks, reading the 27 MB basis from HBM once and from L2 afterwards).  Round 2
+// measured one launch per 96..128 frames at 0.49..0.53 of the HBM peak by CUDA events, 10 us of each launch being ramp
+// and drain of the 148 x 576-thread grid; groups of about 1024 frames amortise that: 0.61 (4096 frames at 1024x1024) /
+// 0.62 (12000 at 256x256) per launch, and the step gains 4..8 % (profiles/r02m_basis_blocks.txt).  The displacements of
+// such a group, 0.43 MB per frame, no longer stay in L2 for the vertex kernel -- +4 % of the path's HBM bytes at 256x256,
+// +2 % at 1024x1024 -- which the LSU-bound vertex kernel does not notice (7.02 -> 6.99 ms per 12000 frames).
 int basis_group_frames(int chunk, int nframes) {
-  const int cap = (int)env_size("VPB200_BASIS_FRAMES", 96);
+  const int cap = (int)env_size("VPB200_BASIS_FRAMES", 1024);
   const int t = std::max(nframes, 1);
   const int ngroups = (t + cap - 1) / cap;
   const int per_group = (t + ngroups - 1) / ngroups;
@@ -158,9 +163,9 @@ struct ChunkRunner {
   // frames [t0, t0 + n): n <= chunk_cap and inside one basis group.  *used = the stream the chunk runs on.
   int run(int t0, int n, unsigned char* image_dev, unsigned char* mask_dev, cudaStream_t* used) {
     if (ex_dev) {
-      // The expression coefficients of a basis group are contracted on `st`, lazily and in pieces of 128 frames (one
-      // tcgen05 launch): only as far as this chunk needs.  A short first chunk (the push gather's plan) then starts
-      // after one launch instead of after the whole group; a chunk that spans the group gets it in one call as before.
+      // The expression coefficients of a basis group are contracted on `st` when its first chunk is issued: the whole
+      // group in one launch by default, or lazily in pieces of VPB200_BASIS_PIECE frames (only as far as this chunk
+      // needs: a short first chunk of the push gather's plan then starts sooner).
       const int g0 = t0 - t0 % group, gend = std::min(g0 + group, nframes);
       if (t0 == g0) {
         if (aux_used) {                 // chunks on the auxiliary stream may still read the previous group
@@ -170,7 +175,8 @@ struct ChunkRunner {
         basis_upto = g0;
       }
       if (basis_upto < t0 + n) {
-        const int upto = std::min(gend, g0 + (t0 + n - g0 + 127) / 128 * 128);
+        static const int piece = (int)env_size("VPB200_BASIS_PIECE", 1 << 20);
+        const int upto = (int)std::min<long long>(gend, g0 + (long long)(t0 + n - g0 + piece - 1) / piece * piece);
         prof.begin(kProfBasis);
         VP_TRY(launch_basis(m, ex_dev + (size_t)basis_upto * VP_N_EX,
                             m->ws_disp.as<float>() + (size_t)(basis_upto - g0) * m->rows_pad, upto - basis_upto, st));

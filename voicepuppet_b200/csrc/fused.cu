@@ -39,7 +39,7 @@ struct FusedArgs {
   unsigned long long* keys;     // [frames][h * w]
   EpochKey km;
   int h, w;
-  int inline_max;               // see raster_walk.cuh
+  int inline_max, group, group_min;  // see raster_walk.cuh
 };
 
 // E phase for one frame: the tile's owned triangles against the frame's z-buffer.
@@ -47,7 +47,7 @@ struct FusedArgs {
 // original index = the key's low bits); rec: this warp's 4 x 32 float4 staging of triangle set-ups.
 __device__ __forceinline__ void raster_owned(const float4* __restrict__ scr, const uint2* __restrict__ s_tri, int nt,
                                              float4 (*rec)[32], unsigned long long* __restrict__ keys,
-                                             const EpochKey& km, int h, int w, int tid, int inline_max) {
+                                             const EpochKey& km, int h, int w, int tid, int inline_max, int group, int group_min) {
   const unsigned lane = (unsigned)tid & 31u;
   const int wm1 = w - 1, hm1 = h - 1;
   for (int p0 = 0; p0 < nt; p0 += kTileV) {  // nt is CTA-uniform: warp-uniform trip count
@@ -85,7 +85,7 @@ __device__ __forceinline__ void raster_owned(const float4* __restrict__ scr, con
         }
       }
     }
-    walk_boxes(s, key, n, inline_max, rec, keys, w, lane);
+    walk_boxes(s, key, n, inline_max, group, group_min, rec, keys, w, lane);
   }
 }
 
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kTileV, MIN_BLOCKS) fused_tile_kernel(const Fu
     }
     __syncthreads();
     // ---- E: the tile's own triangles of frame f (s_scr[buf] is rewritten two barriers from now) -----
-    raster_owned(s_scr[buf], s_tri, nt, s_rec[tid >> 5], a.keys + (size_t)f * npix, a.km, a.h, a.w, tid, a.inline_max);
+    raster_owned(s_scr[buf], s_tri, nt, s_rec[tid >> 5], a.keys + (size_t)f * npix, a.km, a.h, a.w, tid, a.inline_max, a.group, a.group_min);
   }
 }
 
@@ -257,6 +257,8 @@ int launch_fused(vp_model* m, const float* disp_dev, int nframes, const void* fr
   a.h = res;
   a.w = res;
   a.inline_max = inline_box_pixels();
+  a.group = walk_group_lanes();
+  a.group_min = walk_group_min_pixels();
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   const int minb = 5, waves = 2;   // measured best of 4 / 5 / 6 CTAs per SM and 1..4 waves (profiles/r02c_fused_ablation.txt)

@@ -20,6 +20,8 @@ int launch_scatter_generic(int mode, const float* vertices, size_t frame_stride,
 // z-buffer is cleared only when the epoch counter wraps (epoch_limit) or the buffer is reallocated.
 uint32_t epoch_limit(int ntri);
 int inline_box_pixels();
+int walk_group_lanes();
+int walk_group_min_pixels();
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
                           unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
                           int w, cudaStream_t st);

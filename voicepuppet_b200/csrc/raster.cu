@@ -68,6 +68,21 @@ int inline_box_pixels() {
   return v;
 }
 
+// Lanes per group of the scatter kernel's group walk (0 = every lane walks its own box), see raster_walk.cuh.
+int walk_group_lanes() {
+  static const int v = [] {
+    const char* e = std::getenv("VPB200_WALK_GROUP");
+    const int g = e ? std::atoi(e) : 4;
+    return (g == 2 || g == 4 || g == 8 || g == 16 || g == 32) ? g : 0;
+  }();
+  return v;
+}
+
+int walk_group_min_pixels() {
+  static const int v = [] { const char* e = std::getenv("VPB200_WALK_GROUP_MIN"); return e ? std::atoi(e) : 320; }();
+  return v;
+}
+
 int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* triangles,
                           unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
                           int w, cudaStream_t st) {
@@ -95,8 +110,20 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
     a.h = h;
     a.w = w;
     a.inline_max = inline_box_pixels();
-    static const int minb = [] { const char* e = std::getenv("VPB200_SCATTER_MINB"); return e ? std::atoi(e) : 5; }();  // 48 registers, 40 warps/SM: +3 % over 64 / 32
-    if (minb >= 6)
+    a.group = walk_group_lanes();
+    a.group_min = walk_group_min_pixels();
+    // Up to 512x512: 48 registers, 40 warps/SM (+3..9 % over 64 / 32), every lane walks its own box.  From 768x768:
+    // the group walk (raster_walk.cuh; 1024x1024: 4.02 -> 3.52 us per frame) in the 64-register build it wants (-6 %).
+    // At 256x256 the mere presence of the group path costs 2 %, hence two instantiations.
+    static const int minb_env = [] { const char* e = std::getenv("VPB200_SCATTER_MINB"); return e ? std::atoi(e) : 0; }();
+    static const long long group_res = [] { const char* e = std::getenv("VPB200_WALK_GROUP_RES"); return e ? std::atoll(e) : 768ll; }();
+    const bool large = (long long)h * w >= group_res * group_res;
+    const int minb = minb_env ? minb_env : (large ? 4 : 5);
+    if (a.group > 0 && large && minb <= 4)
+      raster_scatter_packed_kernel<4, true><<<grid, kRasterBlock, 0, st>>>(a);
+    else if (a.group > 0 && large)
+      raster_scatter_packed_kernel<5, true><<<grid, kRasterBlock, 0, st>>>(a);
+    else if (minb >= 6)
       raster_scatter_packed_kernel<6><<<grid, kRasterBlock, 0, st>>>(a);
     else if (minb == 5)
       raster_scatter_packed_kernel<5><<<grid, kRasterBlock, 0, st>>>(a);

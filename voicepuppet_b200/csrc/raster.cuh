@@ -198,9 +198,10 @@ struct ScatterArgs {
   unsigned stride;              // float4 per frame
   int ntri, nframes, frames_per_block, h, w;
   int inline_max;               // boxes up to this many pixels are walked by their own lane, larger ones flattened
+  int group, group_min;         // lanes (0 / 4 / 8) that walk each other's boxes together, and the pixels a warp's boxes must hold for it (raster_walk.cuh)
 };
 
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool GROUP = false>
 __global__ void __launch_bounds__(kRasterBlock, MIN_BLOCKS)
 raster_scatter_packed_kernel(const ScatterArgs a) {
   __shared__ float4 s_rec[kRasterBlock / 32][4][32];  // per-warp staging of the flattened large boxes (raster_walk.cuh)
@@ -218,7 +219,7 @@ raster_scatter_packed_kernel(const ScatterArgs a) {
   for (int frame = frame_begin; frame < frame_end; ++frame) {
     // 32-bit element offsets (the launcher checks nframes * stride and nframes * ntri fit)
     const unsigned vbase = (unsigned)frame * a.stride;
-    unsigned long long* keys = a.keys + (size_t)frame * npix;
+    unsigned long long* keys = a.keys + (size_t)(unsigned)frame * npix;
     Candidate c;
     c.n = 0;
     c.key = 0ull;
@@ -257,7 +258,7 @@ raster_scatter_packed_kernel(const ScatterArgs a) {
       }
     }
 
-    walk_boxes(c.s, c.key, c.n, a.inline_max, s_rec[threadIdx.x >> 5], keys, a.w, lane);
+    walk_boxes(c.s, c.key, c.n, a.inline_max, GROUP ? a.group : 0, a.group_min, s_rec[threadIdx.x >> 5], keys, a.w, lane);
   }
 }
 

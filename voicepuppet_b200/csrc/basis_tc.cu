@@ -404,8 +404,7 @@ int launch_basis_tc(vp_model* m, const float* ex_dev, float* disp_dev, int nfram
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
   const int grid = std::min(ntiles, sms);
-  // streaming stores (default-policy stores measured equal in round 1); VPB200_BASIS_STORE=1 selects them for the A/B
-  static const int store_policy = [] { const char* e = std::getenv("VPB200_BASIS_STORE"); return e ? std::atoi(e) : 0; }();
+  const int store_policy = 0;  // streaming stores (default-policy stores measured equal in round 1 and again in round 2, call 27)
   const int n_cap = (std::min(nframes, kTcN) + 15) & ~15;
   basis_tc_kernel<<<grid, kTcThreads, tc_smem_bytes(n_cap), st>>>(map, ex_dev, disp_dev, nframes, m->rows_pad, ntiles,
                                                                   trace_dev, store_policy);

@@ -87,12 +87,18 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
                           unsigned long long* keys, uint32_t* tri_color, uint32_t epoch, int nframes, int ntri, int h,
                           int w, cudaStream_t st) {
   if (ntri == 0 || nframes == 0) return VP_OK;
+  // From 768x768 the group walk (raster_walk.cuh; 1024x1024: 4.02 -> 3.52 us per frame) in a 64-register build, below it
+  // every lane walks its own box in a 48-register build (40 warps/SM: +3..9 % there; the mere presence of the group path
+  // costs 2 % at 256x256, hence two instantiations).  CTAs of 128 threads retire sooner than the 256 of round 1 (+1..3 %),
+  // and the triangle indices are loaded once for 8 frames (4 at large frames, where 8 loses 1.5 %): profiles/r02o_group_walk.txt.
+  static const long long group_res = [] { const char* e = std::getenv("VPB200_WALK_GROUP_RES"); return e ? std::atoll(e) : 768ll; }();
+  const bool large = (long long)h * w >= group_res * group_res;
   static const int fpb_env = [] { const char* e = std::getenv("VPB200_SCATTER_FPB"); return e ? std::atoi(e) : 0; }();
-  const int fpb = fpb_env > 0 ? fpb_env : (nframes >= 32 ? 4 : (nframes >= 16 ? 2 : 1));  // frames per block: indices are loaded once
-  dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, (nframes + fpb - 1) / fpb);
+  const int fpb = fpb_env > 0 ? fpb_env : (nframes >= 32 ? (large ? 4 : 8) : (nframes >= 16 ? 2 : 1));
   const bool fits32 = (unsigned long long)nframes * frame_stride < (1ull << 32) &&
                       (unsigned long long)nframes * (unsigned long long)ntri < (1ull << 32);
   if (!fits32) {  // the generic template on the packed records (64-bit offsets)
+    dim3 grid((ntri + kRasterBlock - 1) / kRasterBlock, (nframes + fpb - 1) / fpb);
     PackedMesh mesh{vrec, triangles, frame_stride};
     raster_scatter_kernel<kModeColors, PackedMesh, EpochKey><<<grid, kRasterBlock, 0, st>>>(
         mesh, make_epoch_key(ntri, epoch), keys, tri_color, ntri, nframes, fpb, h, w, 1);
@@ -112,23 +118,11 @@ int launch_scatter_packed(const float4* vrec, size_t frame_stride, const int4* t
     a.inline_max = inline_box_pixels();
     a.group = walk_group_lanes();
     a.group_min = walk_group_min_pixels();
-    // Up to 512x512: 48 registers, 40 warps/SM (+3..9 % over 64 / 32), every lane walks its own box.  From 768x768:
-    // the group walk (raster_walk.cuh; 1024x1024: 4.02 -> 3.52 us per frame) in the 64-register build it wants (-6 %).
-    // At 256x256 the mere presence of the group path costs 2 %, hence two instantiations.
-    static const int minb_env = [] { const char* e = std::getenv("VPB200_SCATTER_MINB"); return e ? std::atoi(e) : 0; }();
-    static const long long group_res = [] { const char* e = std::getenv("VPB200_WALK_GROUP_RES"); return e ? std::atoll(e) : 768ll; }();
-    const bool large = (long long)h * w >= group_res * group_res;
-    const int minb = minb_env ? minb_env : (large ? 4 : 5);
-    if (a.group > 0 && large && minb <= 4)
-      raster_scatter_packed_kernel<4, true><<<grid, kRasterBlock, 0, st>>>(a);
-    else if (a.group > 0 && large)
-      raster_scatter_packed_kernel<5, true><<<grid, kRasterBlock, 0, st>>>(a);
-    else if (minb >= 6)
-      raster_scatter_packed_kernel<6><<<grid, kRasterBlock, 0, st>>>(a);
-    else if (minb == 5)
-      raster_scatter_packed_kernel<5><<<grid, kRasterBlock, 0, st>>>(a);
+    dim3 grid((ntri + kScatterBlock - 1) / kScatterBlock, (nframes + fpb - 1) / fpb);
+    if (a.group > 0 && large)
+      raster_scatter_packed_kernel<8, true><<<grid, kScatterBlock, 0, st>>>(a);
     else
-      raster_scatter_packed_kernel<4><<<grid, kRasterBlock, 0, st>>>(a);
+      raster_scatter_packed_kernel<10, false><<<grid, kScatterBlock, 0, st>>>(a);
   }
   VP_LAUNCH_CHECK();
   return VP_OK;

@@ -17,6 +17,7 @@
 namespace vp {
 
 constexpr int kRasterBlock = 256;
+constexpr int kScatterBlock = 128;  // CTA of the packed scatter kernel
 constexpr int kSmallBox = 12;  // boxes up to this many pixels are walked by the owning lane
 
 enum RasterMode { kModeColors = 0, kModeTriangles = 1 };
@@ -201,11 +202,11 @@ struct ScatterArgs {
   int group, group_min;         // lanes (0 / 4 / 8) that walk each other's boxes together, and the pixels a warp's boxes must hold for it (raster_walk.cuh)
 };
 
-template <int MIN_BLOCKS, bool GROUP = false>
-__global__ void __launch_bounds__(kRasterBlock, MIN_BLOCKS)
+template <int MIN_BLOCKS, bool GROUP>
+__global__ void __launch_bounds__(kScatterBlock, MIN_BLOCKS)
 raster_scatter_packed_kernel(const ScatterArgs a) {
-  __shared__ float4 s_rec[kRasterBlock / 32][4][32];  // per-warp staging of the flattened large boxes (raster_walk.cuh)
-  const int f = blockIdx.x * kRasterBlock + threadIdx.x;
+  __shared__ float4 s_rec[kScatterBlock / 32][4][32];  // per-warp staging of the group walk / the flattened large boxes (raster_walk.cuh)
+  const int f = blockIdx.x * kScatterBlock + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   const bool valid = f < a.ntri;
   int4 t = make_int4(0, 0, 0, 0);

@@ -114,6 +114,7 @@ struct ChunkRunner {
   const FrameParams* params_dev = nullptr;
   const char* fconst = nullptr;
   bool dual = false, aux_used = false, aux_needs_basis = false, fused = false;
+  bool planned = false;  // the caller gave a chunk plan and waits on per-chunk events
   int issued = 0;
   int basis_upto = 0;   // frames [group start, basis_upto) of the current basis group are contracted
 
@@ -176,7 +177,10 @@ struct ChunkRunner {
       }
       if (basis_upto < t0 + n) {
         static const int piece = (int)env_size("VPB200_BASIS_PIECE", 1 << 20);
-        const int upto = (int)std::min<long long>(gend, g0 + (long long)(t0 + n - g0 + piece - 1) / piece * piece);
+        int upto = (int)std::min<long long>(gend, g0 + (long long)(t0 + n - g0 + piece - 1) / piece * piece);
+        // a caller with a chunk plan (push gather, notify) wants its first, short chunk out early: contract just the
+        // frames that chunk needs first (one 128-frame block), the rest of the first group with the next chunk
+        if (planned && g0 == 0 && basis_upto == 0) upto = std::min(upto, (t0 + n + 127) / 128 * 128);
         prof.begin(kProfBasis);
         VP_TRY(launch_basis(m, ex_dev + (size_t)basis_upto * VP_N_EX,
                             m->ws_disp.as<float>() + (size_t)(basis_upto - g0) * m->rows_pad, upto - basis_upto, st));
@@ -293,6 +297,7 @@ static int render_sequence_dev_impl(vp_model* m, int nframes, const float* ex_de
   const int nchunks = plan ? nplan : (nframes + chunk - 1) / chunk;
   const size_t npix = (size_t)res * res;
   ChunkRunner run(m, st);
+  run.planned = plan != nullptr;
   int rc = run.init(nframes, res, chunk, nchunks, ex_dev, reinterpret_cast<const FrameParams*>(params_dev),
                     rotate_shape_first);
   int t0 = 0;

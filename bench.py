@@ -411,8 +411,20 @@ def measure_single_gpu(env, name, steps, warmup, want_clocks=False, e2e_steps=No
         'launches_per_step': kd['launches'],
         'note': 'dominant kernel by duration over the step; durations are CUDA events around every launch of the '
                 'timed chunk plan (one stream instead of two so the spans do not overlap); per-kernel figures of the '
-                'whole path under "kernels"'}
+                'whole path under "kernels"',
+        'limiter': LIMITERS.get(dom)}
   return out
+
+
+# What ncu and the microbenchmarks say bounds each kernel (profiles/): the HBM fraction above is the
+# contract's yardstick, not always the kernel's own limit.
+LIMITERS = {
+    'basis': 'store path of the displacements (4.4 TB/s of writes per further 128-frame block) + ramp / drain of the launch',
+    'vertex': 'instruction issue / LSU (shared-memory position gathers): 68 % issue-active, moves little data',
+    'scatter': 'sectors touched by the 64-bit REDG.MAX reductions (1.64 cycles per lane spread, 0.76 in runs of 4: '
+               'tools/diag_redg.cu) and then instruction issue (80 % issue-active): moves little data',
+    'resolve': 'HBM',
+}
 
 
 def tri_id_report(env):

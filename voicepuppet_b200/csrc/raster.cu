@@ -132,9 +132,19 @@ int launch_resolve_packed(const unsigned long long* keys, const uint32_t* tri_co
                           cudaStream_t st) {
   const size_t npix = (size_t)h * w;
   if (nframes == 0 || npix == 0) return VP_OK;
-  dim3 grid((unsigned)((npix / 4 + 255) / 256), nframes);
-  resolve_packed_kernel<<<grid, 256, 0, st>>>(keys, make_epoch_key(ntri, epoch), tri_color, image, mask,
-                                              ntri, npix);
+  // pixels per thread: 8 (two groups of 4, all key loads in flight before the first dependent gather) from 512x512 and in
+  // long launches -- resolve -9 % at 1024x1024 (0.80 -> 0.88 of the HBM peak), -8 % at 512x512, step +1 % at 3000 x 256x256 --
+  // 4 in the short launches of a 75-frame clip; 16 loses everywhere (profiles/r02o_group_walk.txt, calls 32-33)
+  static const int px_env = [] { const char* e = std::getenv("VPB200_RESOLVE_PX"); return e ? std::atoi(e) : 0; }();
+  const int px = px_env ? px_env : ((npix >= 512u * 512u || nframes >= 64) ? 8 : 4);
+  const EpochKey km = make_epoch_key(ntri, epoch);
+  if (px >= 8) {
+    dim3 grid((unsigned)((npix / 4 + 511) / 512), nframes);
+    resolve_packed_kernel<2><<<grid, 256, 0, st>>>(keys, km, tri_color, image, mask, ntri, npix);
+  } else {
+    dim3 grid((unsigned)((npix / 4 + 255) / 256), nframes);
+    resolve_packed_kernel<1><<<grid, 256, 0, st>>>(keys, km, tri_color, image, mask, ntri, npix);
+  }
   VP_LAUNCH_CHECK();
   return VP_OK;
 }

@@ -323,44 +323,61 @@ __global__ void resolve_triangles_kernel(const unsigned long long* __restrict__ 
   weights[3 * p + 2] = w2;
 }
 
-// Fused-path resolve: 4 pixels per thread, one tri_color gather per covered pixel (by original triangle index), every pixel
-// written (uncovered or stale-epoch key -> 0), so neither the image nor the z-buffer needs a clear.
-// Requires (h*w) % 4 == 0.
+// Fused-path resolve: NG (1 or 2) groups of 4 consecutive pixels per thread (the groups of a thread lie 256 groups apart, so
+// that every load and store instruction of a warp stays contiguous), one tri_color gather per covered pixel (by original
+// triangle index), every pixel written (uncovered or stale-epoch key -> 0), so neither the image nor the z-buffer needs a
+// clear.  Requires (h*w) % 4 == 0.
+template <int NG>
 __global__ void __launch_bounds__(256)
 resolve_packed_kernel(const unsigned long long* __restrict__ keys, EpochKey km,
                       const uint32_t* __restrict__ tri_color, unsigned char* __restrict__ image,
                       unsigned char* __restrict__ mask, int ntri, size_t npix) {
   const int frame = blockIdx.y;
-  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
-  if (q * 4 >= npix) return;
-  const size_t base = (size_t)frame * npix + q * 4;
-  const ulonglong2 k01 = __ldcs(reinterpret_cast<const ulonglong2*>(keys + base));
-  const ulonglong2 k23 = __ldcs(reinterpret_cast<const ulonglong2*>(keys + base + 2));
-  const unsigned long long k[4] = {k01.x, k01.y, k23.x, k23.y};
+  const size_t q0 = (size_t)blockIdx.x * (256 * NG) + threadIdx.x;  // first group of 4 pixels
   const uint32_t* tc = tri_color + (size_t)frame * ntri;
-  uint32_t col[4];
+  unsigned long long k[NG][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool live = k[i] >= km.epoch_field;  // written during this chunk
-    const uint32_t t = km.tri_mask - (static_cast<uint32_t>(k[i]) & km.tri_mask);  // winner's ORIGINAL index
-    // neighbouring pixels of one triangle carry the same key (flat depth): one gather chain serves them all
-    // (at 1024x1024 a triangle covers ~8 pixels, so this removes about half of the dependent gathers)
-    if (i > 0 && k[i] == k[i - 1])
-      col[i] = col[i - 1];
-    else
-      col[i] = live ? __ldg(tc + t) : 0u;
+  for (int g = 0; g < NG; ++g) {  // all key loads in flight before the first dependent gather
+    const size_t q = q0 + (size_t)g * 256;
+    if (q * 4 < npix) {
+      const size_t base = (size_t)frame * npix + q * 4;
+      const ulonglong2 k01 = __ldcs(reinterpret_cast<const ulonglong2*>(keys + base));
+      const ulonglong2 k23 = __ldcs(reinterpret_cast<const ulonglong2*>(keys + base + 2));
+      k[g][0] = k01.x;
+      k[g][1] = k01.y;
+      k[g][2] = k23.x;
+      k[g][3] = k23.y;
+    }
   }
-  // 12 bytes of RGB for 4 pixels as three 32-bit words
-  const uint32_t w0 = (col[0] & 0xFFFFFFu) | ((col[1] & 0xFFu) << 24);
-  const uint32_t w1 = ((col[1] >> 8) & 0xFFFFu) | ((col[2] & 0xFFFFu) << 16);
-  const uint32_t w2 = ((col[2] >> 16) & 0xFFu) | ((col[3] & 0xFFFFFFu) << 8);
-  uint32_t* out = reinterpret_cast<uint32_t*>(image + base * 3);
-  __stcs(out, w0);
-  __stcs(out + 1, w1);
-  __stcs(out + 2, w2);
-  if (mask != nullptr) {
-    const uint32_t m = (col[0] >> 24) | ((col[1] >> 24) << 8) | ((col[2] >> 24) << 16) | ((col[3] >> 24) << 24);
-    __stcs(reinterpret_cast<uint32_t*>(mask + base), m);
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    const size_t q = q0 + (size_t)g * 256;
+    if (q * 4 >= npix) break;
+    const size_t base = (size_t)frame * npix + q * 4;
+    uint32_t col[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool live = k[g][i] >= km.epoch_field;  // written during this chunk
+      const uint32_t t = km.tri_mask - (static_cast<uint32_t>(k[g][i]) & km.tri_mask);  // winner's ORIGINAL index
+      // neighbouring pixels of one triangle carry the same key (flat depth): one gather chain serves them all
+      // (at 1024x1024 a triangle covers ~8 pixels, so this removes about half of the dependent gathers)
+      if (i > 0 && k[g][i] == k[g][i - 1])
+        col[i] = col[i - 1];
+      else
+        col[i] = live ? __ldg(tc + t) : 0u;
+    }
+    // 12 bytes of RGB for 4 pixels as three 32-bit words
+    const uint32_t w0 = (col[0] & 0xFFFFFFu) | ((col[1] & 0xFFu) << 24);
+    const uint32_t w1 = ((col[1] >> 8) & 0xFFFFu) | ((col[2] & 0xFFFFu) << 16);
+    const uint32_t w2 = ((col[2] >> 16) & 0xFFu) | ((col[3] & 0xFFFFFFu) << 8);
+    uint32_t* out = reinterpret_cast<uint32_t*>(image + base * 3);
+    __stcs(out, w0);
+    __stcs(out + 1, w1);
+    __stcs(out + 2, w2);
+    if (mask != nullptr) {
+      const uint32_t m = (col[0] >> 24) | ((col[1] >> 24) << 8) | ((col[2] >> 24) << 16) | ((col[3] >> 24) << 24);
+      __stcs(reinterpret_cast<uint32_t*>(mask + base), m);
+    }
   }
 }
 

@@ -112,3 +112,36 @@ def test_stress_4096_frames_at_1024_tensor_core_basis(full_model):
   assert (got.max(axis=2) > 0).mean() > 0.4                      # ~47 % coverage at every size
   del out
   torch.cuda.empty_cache()
+
+
+_WALK_SCRIPT = r'''
+import hashlib, sys
+import numpy as np
+from voicepuppet_b200 import render, synthetic
+full = synthetic.cached_model()
+coeffs = synthetic.make_coeffs(70, seed=31)
+frames = np.asarray(render.render_sequence(coeffs, full, res=int(sys.argv[1]), angles='jitter'))
+print('SHA', hashlib.sha1(frames.tobytes()).hexdigest(), int(frames.any()))
+'''
+
+
+@pytest.mark.parametrize('res', [768, 1024])
+def test_group_walk_equals_lane_local_walk(res):
+  """From 768x768 the scatter kernel walks the boxes of four lanes together (raster_walk.cuh); the walk is chosen once per
+  process, so two child processes render the same 70 frames, one with the group walk (default) and one with every lane
+  walking its own box (VPB200_WALK_GROUP=0): the frames must be the same bytes.  (Each walk is also compared with the
+  CPU reference: test_stress_4096_frames_at_1024_tensor_core_basis samples frames of the default, test_gpu_sequence of the lane-local one.)"""
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  got = {}
+  for group in ('4', '0'):
+    env = dict(os.environ, VPB200_WALK_GROUP=group, PYTHONPATH=root + os.pathsep + os.environ.get('PYTHONPATH', ''))
+    out = subprocess.run([sys.executable, '-c', _WALK_SCRIPT, str(res)], env=env, cwd=root, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith('SHA')][-1].split()
+    assert line[2] == '1'
+    got[group] = line[1]
+  assert got['4'] == got['0']

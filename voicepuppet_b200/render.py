@@ -190,9 +190,10 @@ def push_plan(n_local, world):
   if n_local >= 512:
     # long shards (the 12000-frame configuration: 1500 frames per GPU at 8).  Measured at 2 GPUs
     # (profiles/r02g_multi_n2_*.json): chunks of one basis group (94 frames) cost 8 % against the unchunked
-    # rendering, because every chunk is three launches with a ramp and a tail; so the chunks are 256 frames (the
-    # contraction runs 128 frames per launch inside a chunk), the first one cut 64 + 192 so that the first push
-    # starts early, the last one ending with a 64-frame chunk so that the push left exposed at the end is short.
+    # rendering, because every chunk is three launches with a ramp and a tail; so the chunks are 256 frames, the first
+    # one cut 64 + 192 so that the first push starts early (the library contracts the first 128-frame block of the
+    # basis group on its own for a planned call, the rest of the group in one launch with the second chunk), the last
+    # one ending with a 64-frame chunk so that the push left exposed at the end is short.
     chunk = int(os.environ.get('VPB200_PUSH_CHUNK', '256'))
     first = min(int(os.environ.get('VPB200_PUSH_FIRST', '64')), chunk // 2)
     last = int(os.environ.get('VPB200_PUSH_LAST', '64'))
